@@ -1,0 +1,177 @@
+/*
+ * nk_b200.h -- C ABI of the B200-native dense forward/backward hot path of neuronika.
+ *
+ * This is the drop-in boundary: one C function per
+ * (operator, direction), taking device pointers and sizes, launched asynchronously on
+ * the context's CUDA stream.  A Rust `Forward`/`Backward` node (reference trait objects,
+ * neuronika-variable/src/autograd.rs:7-12, 20-25) keeps `Shared<CuArray>` handles exactly
+ * like the reference's only device node does (cuda/cunode/binary_op/mod.rs:11-82) and
+ * calls one of these functions from `forward()` / `backward()`.
+ *
+ * Conventions
+ *   - every function returns 0 (NK_OK) or a negative nk_status; the message is available
+ *     through nk_last_error().  Nothing aborts or throws across the ABI (the reference
+ *     `.unwrap()`s every CUDA result, cuda/device.rs:36-45; the Rust wrapper does the same
+ *     on our status codes).
+ *   - all tensors are dense, C-order (row-major); images are NCHW (reference layout).
+ *   - `beta` on a backward entry point selects the reference's accumulate protocol:
+ *     beta = 1 -> `grad += ...` (what every reference Backward node does), beta = 0 ->
+ *     overwrite (used by the host for a gradient buffer that is known to be all-zero,
+ *     which gives identical results without the read).
+ *   - element types: NK_F32 (reference type) and NK_BF16 (tensor-core operand type).
+ *   - a context is single-threaded (like the reference's Rc graph, utils.rs:9); use one
+ *     context per host thread / per GPU.
+ *   - there is NO CPU fallback: every entry point fails with NK_ERR_CUDA when no device
+ *     is present.
+ */
+#ifndef NK_B200_H
+#define NK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nk_ctx nk_ctx;
+
+typedef enum {
+  NK_OK = 0,
+  NK_ERR_INVALID_ARG = -1,
+  NK_ERR_CUDA = -2,
+  NK_ERR_NCCL = -3,
+  NK_ERR_OOM = -4,
+  NK_ERR_UNSUPPORTED = -5
+} nk_status;
+
+typedef enum { NK_F32 = 0, NK_BF16 = 1 } nk_dtype;
+
+/* GEMM engine selection (nk_gemm_config): AUTO picks tcgen05 whenever the operands are
+ * bf16 and TMA-addressable, else the SIMT kernel. */
+typedef enum { NK_GEMM_AUTO = 0, NK_GEMM_SIMT = 1, NK_GEMM_TCGEN05 = 2 } nk_gemm_engine;
+
+/* ---- context (replaces cuda::Device, neuronika-variable/src/cuda/device.rs:11-75) ---- */
+int nk_ctx_create(int device, nk_ctx** out);
+int nk_ctx_destroy(nk_ctx* ctx);
+/* adopt an external cudaStream_t (e.g. torch's) so events / NCCL order with our kernels */
+int nk_ctx_set_stream(nk_ctx* ctx, void* cuda_stream);
+void* nk_ctx_stream(nk_ctx* ctx);
+const char* nk_last_error(nk_ctx* ctx);
+const char* nk_version(void);
+int nk_sync(nk_ctx* ctx);
+/* number of kernels this library launched on ctx since creation */
+uint64_t nk_launch_count(nk_ctx* ctx);
+int nk_sm_count(nk_ctx* ctx);
+int nk_gemm_config(nk_ctx* ctx, int engine /* nk_gemm_engine */);
+/* name of the kernel variant the last nk_gemm call used ("tcgen05_nt_128x256", "simt", ...) */
+const char* nk_last_gemm_kernel(nk_ctx* ctx);
+
+/* ---- buffers (replaces cuda::CuArray, cuda/cuarray.rs:10-171) ---- */
+int nk_alloc(nk_ctx* ctx, size_t bytes, void** dptr);      /* zero-filled, like CuArray::zeroed :35 */
+int nk_free(nk_ctx* ctx, void* dptr);
+int nk_h2d(nk_ctx* ctx, void* dst, const void* src, size_t bytes);   /* from_ndarray :114 */
+int nk_d2h(nk_ctx* ctx, void* dst, const void* src, size_t bytes);   /* as_ndarray :101 (blocks) */
+int nk_d2d(nk_ctx* ctx, void* dst, const void* src, size_t bytes);
+int nk_memset0(nk_ctx* ctx, void* dptr, size_t bytes);
+int nk_host_alloc(nk_ctx* ctx, size_t bytes, void** hptr);           /* pinned host memory */
+int nk_host_free(nk_ctx* ctx, void* hptr);
+int nk_fill(nk_ctx* ctx, void* dptr, int dtype, size_t n, float value);
+int nk_cast(nk_ctx* ctx, void* dst, int dst_dtype, const void* src, int src_dtype, size_t n);
+/* CUDA-event stopwatch on the context stream */
+int nk_timer_start(nk_ctx* ctx);
+int nk_timer_stop(nk_ctx* ctx, float* ms);
+
+/* ---- matrix multiply: C = alpha * op(A) . op(B) + beta * C  (row-major, like ndarray's
+ * general_mat_mul call sites: matrix_matrix_mul/mod.rs:33,65,97; matrix_matrix_mul_t/mod.rs:33,65,97)
+ *   op(A) is M x K: transA=0 -> A stored (M,K) lda>=K ; transA=1 -> A stored (K,M) lda>=M
+ *   op(B) is K x N: transB=0 -> B stored (K,N) ldb>=N ; transB=1 -> B stored (N,K) ldb>=K
+ *   mm fwd: NN; mm dA: NT; mm dB: TN; mm_t fwd: NT; mm_t dX: NN; mm_t dW: TN.
+ *   Optional fused epilogue: + bias[N] (row broadcast, Linear fwd) and ReLU. */
+int nk_gemm(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha,
+            const void* A, int64_t lda, const void* B, int64_t ldb, float beta, void* C,
+            int64_t ldc, int ab_dtype, int c_dtype);
+int nk_gemm_bias_act(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K,
+                     float alpha, const void* A, int64_t lda, const void* B, int64_t ldb,
+                     float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype,
+                     const void* bias /* N elements, c_dtype or f32 */, int bias_dtype,
+                     int relu);
+
+/* ---- broadcasting add (addition/mod.rs:39-50, 81-135; utils.rs:97-125, 152-192) ----
+ * shapes are right-aligned, up to NK_MAX_DIMS dims. */
+#define NK_MAX_DIMS 6
+int nk_add_bcast_fwd(nk_ctx* ctx, void* y, const void* l, const void* r, int dtype,
+                     int y_ndim, const int64_t* y_shape, int l_ndim, const int64_t* l_shape,
+                     int r_ndim, const int64_t* r_shape);
+/* dst = beta*dst + unbroadcast(g -> dst_shape) */
+int nk_unbroadcast_acc(nk_ctx* ctx, void* dst, int dst_dtype, int dst_ndim,
+                       const int64_t* dst_shape, const void* g, int g_dtype, int g_ndim,
+                       const int64_t* g_shape, float beta);
+
+/* ---- relu (relu/mod.rs:29-38, 67-79) ---- */
+int nk_relu_fwd(nk_ctx* ctx, void* y, const void* x, size_t n, int dtype);
+int nk_relu_bwd(nk_ctx* ctx, void* dx, const void* x, const void* g, size_t n, int dtype, float beta);
+
+/* ---- softmax / log-softmax along one axis of an (outer, len, inner) view
+ * (softmax/mod.rs:37-53, 84-104; logsoftmax/mod.rs:37-53, 84-102) ---- */
+int nk_softmax_fwd(nk_ctx* ctx, void* y, const void* x, int64_t outer, int64_t len, int64_t inner, int dtype);
+int nk_softmax_bwd(nk_ctx* ctx, void* dx, const void* y, const void* g, int64_t outer, int64_t len,
+                   int64_t inner, int dtype, float beta);
+int nk_log_softmax_fwd(nk_ctx* ctx, void* y, const void* x, int64_t outer, int64_t len, int64_t inner, int dtype);
+int nk_log_softmax_bwd(nk_ctx* ctx, void* dx, const void* y, const void* g, int64_t outer, int64_t len,
+                       int64_t inner, int dtype, float beta);
+
+/* ---- losses and scalar reductions; scalar outputs / seeds are device f32 ----
+ * (squared_error/mod.rs:46-58, 98-122; nll/mod.rs:42-68, 100-133; sum/mod.rs, mean/mod.rs) */
+int nk_mse_fwd(nk_ctx* ctx, float* loss, const void* x, const void* t, size_t n, int dtype, int mean);
+int nk_mse_bwd(nk_ctx* ctx, void* dx, const void* x, const void* t, const float* g, size_t n,
+               int dtype, int mean, float beta);
+int nk_nll_fwd(nk_ctx* ctx, float* loss, const void* logp, const void* target, int64_t n,
+               int64_t c, int dtype, int mean);
+int nk_nll_bwd(nk_ctx* ctx, void* dlogp, const void* target, const float* g, int64_t n, int64_t c,
+               int dtype, int mean, float beta);
+int nk_sum_fwd(nk_ctx* ctx, float* out, const void* x, size_t n, int dtype, int mean);
+int nk_sum_bwd(nk_ctx* ctx, void* dx, const float* g, size_t n, int dtype, int mean, float beta);
+
+/* ---- 2-D constant/zero padding of (planes, H, W) (pad/mod.rs:97-129, 157-182) ---- */
+int nk_pad2d_fwd(nk_ctx* ctx, void* y, const void* x, int64_t planes, int64_t h, int64_t w,
+                 int64_t ph, int64_t pw, float value, int dtype);
+int nk_pad2d_bwd(nk_ctx* ctx, void* dx, const void* g, int64_t planes, int64_t h, int64_t w,
+                 int64_t ph, int64_t pw, int dtype, float beta);
+
+/* ---- 2-D convolution (cross-correlation, NCHW, no implicit padding)
+ * (convolution/mod.rs:85-123 fwd, 146-189 dX, 191-226 dW; arg checks utils.rs:427-496).
+ *   x (N,Cin,H,W)  w (Cout,Cin/groups,kh,kw)  y (N,Cout,Ho,Wo),
+ *   Ho = (H - dh*(kh-1) - 1)/sh + 1.
+ *   fwd optionally fuses + bias[Cout] (the Conv2d layer's (Cout,1,1) bias,
+ *   neuronika-nn/src/lib.rs:774) and ReLU; bwd_kernel optionally also accumulates
+ *   dbias[Cout] += sum_{n,p,q} g. */
+int nk_conv2d_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const void* bias, int relu,
+                  int64_t n, int64_t cin, int64_t h, int64_t wd, int64_t cout, int64_t kh,
+                  int64_t kw, int64_t sh, int64_t sw, int64_t dh, int64_t dw, int64_t groups,
+                  int dtype);
+int nk_conv2d_bwd_input(nk_ctx* ctx, void* dx, const void* g, const void* w, int64_t n,
+                        int64_t cin, int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw,
+                        int64_t sh, int64_t sw, int64_t dh, int64_t dw, int64_t groups, int dtype,
+                        float beta);
+int nk_conv2d_bwd_kernel(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, const void* g,
+                         const void* x, int64_t n, int64_t cin, int64_t h, int64_t wd,
+                         int64_t cout, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t dh,
+                         int64_t dw, int64_t groups, int dtype, float beta);
+/* name of the kernel variant the last conv call used */
+const char* nk_last_conv_kernel(nk_ctx* ctx);
+
+/* ---- SGD (neuronika-optim/src/sgd/mod.rs:191-231, penalty.rs:63-67) ----
+ *   g' = grad_scale*g + 2*l2*w ; no momentum: w -= lr*g' ;
+ *   momentum: buf = mu*buf + (1-damp)*g' ; w -= lr*(nesterov ? g' + mu*buf : buf).
+ *   `buf` (f32, n elements) may be NULL when momentum <= FLT_EPSILON.
+ *   `master` (f32, optional) keeps an f32 copy of bf16 weights: the update is applied to
+ *   master and w receives its rounding.  grad_scale = 1/world_size for data parallel. */
+int nk_sgd_step(nk_ctx* ctx, void* w, int w_dtype, void* g, int g_dtype, float* buf, float* master,
+                size_t n, float lr, float l2, float momentum, float dampening, int nesterov,
+                float grad_scale, int write_back_grad);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NK_B200_H */

@@ -1,0 +1,217 @@
+// Context, buffers, copies: the device-side replacement of cuda::Device / cuda::CuArray
+// (reference: neuronika-variable/src/cuda/device.rs:11-75, cuda/cuarray.rs:10-171).
+#include <stdarg.h>
+
+#include <new>
+
+#include "nk_internal.cuh"
+
+static thread_local std::string g_null_ctx_error;
+
+int nk_set_error(nk_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->last_error = buf;
+  else
+    g_null_ctx_error = buf;
+  return code;
+}
+
+int nk_workspace(nk_ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->workspace_bytes) {
+    if (ctx->workspace) {
+      NK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      NK_CUDA(ctx, cudaFree(ctx->workspace));
+      ctx->workspace = nullptr;
+      ctx->workspace_bytes = 0;
+    }
+    size_t want = bytes < (size_t(8) << 20) ? (size_t(8) << 20) : bytes;
+    NK_CUDA(ctx, cudaMalloc(&ctx->workspace, want));
+    ctx->workspace_bytes = want;
+  }
+  *out = ctx->workspace;
+  return NK_OK;
+}
+
+extern "C" {
+
+const char* nk_version(void) { return "neuronika_b200 0.1 (sm_100a)"; }
+
+int nk_ctx_create(int device, nk_ctx** out) {
+  if (!out) return nk_set_error(nullptr, NK_ERR_INVALID_ARG, "nk_ctx_create: out is NULL");
+  *out = nullptr;
+  nk_ctx* ctx = new (std::nothrow) nk_ctx();
+  if (!ctx) return NK_ERR_OOM;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    int rc = nk_set_error(nullptr, NK_ERR_CUDA, "nk_ctx_create: no CUDA device (%s); this library has no CPU fallback",
+                          cudaGetErrorString(e));
+    delete ctx;
+    return rc;
+  }
+  if (device < 0 || device >= count) {
+    delete ctx;
+    return nk_set_error(nullptr, NK_ERR_INVALID_ARG, "nk_ctx_create: device %d out of range [0,%d)", device, count);
+  }
+  ctx->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    delete ctx;
+    return nk_set_error(nullptr, NK_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    delete ctx;
+    return nk_set_error(nullptr, NK_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
+                        device, prop.major, prop.minor);
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  ctx->own_stream = true;
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  // keep freed blocks cached in the stream-ordered pool: the reference rebuilds its graph (and
+  // re-allocates every node output and gradient) each step, examples/quickstart.rs:216-227
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    ctx->encode_tiled = fn;
+  cudaGetLastError();
+  *out = ctx;
+  return NK_OK;
+}
+
+int nk_ctx_destroy(nk_ctx* ctx) {
+  if (!ctx) return NK_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->workspace) cudaFree(ctx->workspace);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return NK_OK;
+}
+
+int nk_ctx_set_stream(nk_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  return NK_OK;
+}
+
+void* nk_ctx_stream(nk_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+
+const char* nk_last_error(nk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_null_ctx_error.c_str(); }
+
+int nk_sync(nk_ctx* ctx) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NK_OK;
+}
+
+uint64_t nk_launch_count(nk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int nk_sm_count(nk_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int nk_gemm_config(nk_ctx* ctx, int engine) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, engine >= NK_GEMM_AUTO && engine <= NK_GEMM_TCGEN05, "nk_gemm_config: bad engine %d", engine);
+  ctx->gemm_engine = engine;
+  return NK_OK;
+}
+const char* nk_last_gemm_kernel(nk_ctx* ctx) { return ctx ? ctx->last_gemm_kernel : "none"; }
+const char* nk_last_conv_kernel(nk_ctx* ctx) { return ctx ? ctx->last_conv_kernel : "none"; }
+
+int nk_alloc(nk_ctx* ctx, size_t bytes, void** dptr) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, dptr != nullptr, "nk_alloc: dptr is NULL");
+  *dptr = nullptr;
+  if (bytes == 0) bytes = 16;
+  NK_CUDA(ctx, cudaMallocAsync(dptr, bytes, ctx->stream));
+  NK_CUDA(ctx, cudaMemsetAsync(*dptr, 0, bytes, ctx->stream));
+  return NK_OK;
+}
+
+int nk_free(nk_ctx* ctx, void* dptr) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  if (!dptr) return NK_OK;
+  NK_CUDA(ctx, cudaFreeAsync(dptr, ctx->stream));
+  return NK_OK;
+}
+
+int nk_h2d(nk_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  if (bytes == 0) return NK_OK;
+  NK_REQUIRE(ctx, dst && src, "nk_h2d: NULL pointer");
+  NK_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return NK_OK;
+}
+
+int nk_d2h(nk_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  if (bytes == 0) return NK_OK;
+  NK_REQUIRE(ctx, dst && src, "nk_d2h: NULL pointer");
+  NK_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  NK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NK_OK;
+}
+
+int nk_d2d(nk_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  if (bytes == 0) return NK_OK;
+  NK_REQUIRE(ctx, dst && src, "nk_d2d: NULL pointer");
+  NK_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return NK_OK;
+}
+
+int nk_memset0(nk_ctx* ctx, void* dptr, size_t bytes) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  if (bytes == 0) return NK_OK;
+  NK_REQUIRE(ctx, dptr, "nk_memset0: NULL pointer");
+  NK_CUDA(ctx, cudaMemsetAsync(dptr, 0, bytes, ctx->stream));
+  return NK_OK;
+}
+
+int nk_host_alloc(nk_ctx* ctx, size_t bytes, void** hptr) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, hptr != nullptr, "nk_host_alloc: hptr is NULL");
+  NK_CUDA(ctx, cudaMallocHost(hptr, bytes ? bytes : 16));
+  return NK_OK;
+}
+
+int nk_host_free(nk_ctx* ctx, void* hptr) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  if (hptr) NK_CUDA(ctx, cudaFreeHost(hptr));
+  return NK_OK;
+}
+
+int nk_timer_start(nk_ctx* ctx) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return NK_OK;
+}
+
+int nk_timer_stop(nk_ctx* ctx, float* ms) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, ms != nullptr, "nk_timer_stop: ms is NULL");
+  NK_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  NK_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+  NK_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return NK_OK;
+}
+
+}  // extern "C"

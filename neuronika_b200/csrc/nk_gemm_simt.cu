@@ -1,0 +1,195 @@
+// CUDA-core GEMM engine: C = alpha * op(A).op(B) + beta*C (+bias, ReLU), f32 FFMA accumulate.
+// This is the parity-grade path for f32 tensors (tcgen05 has no true-f32 kind) and the fallback
+// for operands TMA cannot address (leading dimension not a multiple of 16 bytes, e.g. the
+// (N, 10) logits of config 4).  Reference call sites: matrix_matrix_mul/mod.rs:33,65,97 and
+// matrix_matrix_mul_t/mod.rs:33,65,97 (general_mat_mul).
+// Tiling: 64x64x16 per CTA, 256 threads, 4x4 register micro-tile, split-K over gridDim.z into an
+// f32 workspace when the (M, N) grid alone cannot fill the 148 SMs.
+#include "nk_internal.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+constexpr int kThreads = 256;
+
+struct Epilogue {
+  float alpha, beta;
+  const void* bias;
+  int bias_bf16;
+  int relu;
+};
+
+template <typename TC>
+__device__ __forceinline__ void store_out(TC* C, int64_t ldc, int64_t m, int64_t n, float acc, const Epilogue& ep) {
+  float v = ep.alpha * acc;
+  if (ep.beta != 0.f) v += ep.beta * nk_to_f32<TC>(C[m * ldc + n]);
+  if (ep.bias)
+    v += ep.bias_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(ep.bias)[n])
+                      : static_cast<const float*>(ep.bias)[n];
+  if (ep.relu) v = v > 0.f ? v : 0.f;
+  C[m * ldc + n] = nk_from_f32<TC>(v);
+}
+
+template <typename TAB, typename TC, bool TA, bool TB>
+__global__ void __launch_bounds__(kThreads) gemm_simt_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
+                                                            TC* __restrict__ C, float* __restrict__ partial,
+                                                            int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                                                            int64_t ldc, int64_t k_per_split, Epilogue ep) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = int64_t(blockIdx.y) * BM, n0 = int64_t(blockIdx.x) * BN;
+  const int64_t k_begin = int64_t(blockIdx.z) * k_per_split;
+  int64_t k_end = k_begin + k_per_split;
+  if (k_end > K) k_end = K;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += BK) {
+    // A tile (BM x BK): 1024 elements, 4 per thread
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + r * kThreads;
+      int mm, kk;
+      if (TA) {  // stored (K, M): consecutive threads along m
+        kk = idx / BM;
+        mm = idx % BM;
+      } else {  // stored (M, K): consecutive threads along k
+        mm = idx / BK;
+        kk = idx % BK;
+      }
+      const int64_t gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < k_end) v = nk_to_f32<TAB>(TA ? A[gk * lda + gm] : A[gm * lda + gk]);
+      As[kk][mm] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + r * kThreads;
+      int nn, kk;
+      if (TB) {  // stored (N, K): consecutive threads along k
+        nn = idx / BK;
+        kk = idx % BK;
+      } else {  // stored (K, N): consecutive threads along n
+        kk = idx / BN;
+        nn = idx % BN;
+      }
+      const int64_t gn = n0 + nn, gk = k0 + kk;
+      float v = 0.f;
+      if (gn < N && gk < k_end) v = nk_to_f32<TAB>(TB ? B[gn * ldb + gk] : B[gk * ldb + gn]);
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t m = m0 + ty * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int64_t n = n0 + tx * TN + j;
+      if (n >= N) continue;
+      if (partial)
+        partial[(int64_t(blockIdx.z) * M + m) * N + n] = acc[i][j];
+      else
+        store_out<TC>(C, ldc, m, n, acc[i][j], ep);
+    }
+  }
+}
+
+template <typename TC>
+__global__ void __launch_bounds__(kThreads) splitk_reduce_kernel(TC* __restrict__ C, const float* __restrict__ partial,
+                                                                int64_t M, int64_t N, int64_t ldc, int splits,
+                                                                Epilogue ep) {
+  const int64_t total = M * N;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[int64_t(z) * total + i];
+    store_out<TC>(C, ldc, i / N, i % N, s, ep);
+  }
+}
+
+template <typename TAB, typename TC>
+int launch(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+           const void* B, int64_t ldb, void* C, int64_t ldc, Epilogue ep) {
+  const int64_t gm = (M + BM - 1) / BM, gn = (N + BN - 1) / BN;
+  NK_REQUIRE(ctx, gm <= 65535, "nk_gemm(simt): M too large");
+  // split-K when the output grid underfills the machine and K is deep
+  int splits = 1;
+  const int64_t tiles = gm * gn;
+  if (tiles < ctx->sm_count && K >= 512) {
+    int64_t s = (2 * int64_t(ctx->sm_count) + tiles - 1) / tiles;
+    const int64_t max_s = K / 128;
+    if (s > max_s) s = max_s;
+    if (s > 64) s = 64;
+    if (s > 1) splits = int(s);
+  }
+  int64_t k_per_split = (K + splits - 1) / splits;
+  k_per_split = (k_per_split + BK - 1) / BK * BK;
+  splits = int((K + k_per_split - 1) / k_per_split);
+  if (splits < 1) splits = 1;
+  float* partial = nullptr;
+  if (splits > 1) {
+    int rc = nk_workspace(ctx, size_t(splits) * size_t(M) * size_t(N) * sizeof(float), (void**)&partial);
+    if (rc) return rc;
+  }
+  dim3 grid((unsigned)gn, (unsigned)gm, (unsigned)splits);
+  const TAB* a = static_cast<const TAB*>(A);
+  const TAB* b = static_cast<const TAB*>(B);
+  TC* c = static_cast<TC*>(C);
+#define NK_L(TA_, TB_) \
+  gemm_simt_kernel<TAB, TC, TA_, TB_><<<grid, kThreads, 0, ctx->stream>>>(a, b, c, partial, M, N, K, lda, ldb, ldc, k_per_split, ep)
+  if (!transA && !transB)
+    NK_L(false, false);
+  else if (!transA && transB)
+    NK_L(false, true);
+  else if (transA && !transB)
+    NK_L(true, false);
+  else
+    NK_L(true, true);
+#undef NK_L
+  NK_LAUNCHED(ctx, "gemm_simt");
+  if (splits > 1) {
+    int64_t blocks = (M * N + kThreads - 1) / kThreads;
+    if (blocks > int64_t(ctx->sm_count) * 8) blocks = int64_t(ctx->sm_count) * 8;
+    splitk_reduce_kernel<TC><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(c, partial, M, N, ldc, splits, ep);
+    NK_LAUNCHED(ctx, "gemm_simt_splitk_reduce");
+  }
+  return NK_OK;
+}
+
+}  // namespace
+
+int nk_gemm_simt(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
+                 int64_t lda, const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype,
+                 int c_dtype, const void* bias, int bias_dtype, int relu) {
+  Epilogue ep{alpha, beta, bias, bias_dtype == NK_BF16, relu};
+  ctx->last_gemm_kernel = "simt_64x64x16";
+  if (ab_dtype == NK_F32 && c_dtype == NK_F32)
+    return launch<float, float>(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, ep);
+  if (ab_dtype == NK_BF16 && c_dtype == NK_BF16)
+    return launch<__nv_bfloat16, __nv_bfloat16>(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, ep);
+  if (ab_dtype == NK_BF16 && c_dtype == NK_F32)
+    return launch<__nv_bfloat16, float>(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, ep);
+  return launch<float, __nv_bfloat16>(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, ep);
+}

@@ -1,0 +1,464 @@
+// tcgen05 GEMM engine (sm_100a): C = alpha * op(A).op(B) + beta*C (+bias[n], ReLU)
+// bf16 operands, f32 accumulation in tensor memory, f32 or bf16 output.
+//
+// Serves the three GEMM forms of every matmul node:
+//   NT  Y  = X.W^T   (MatrixMatrixMulT::forward, matrix_matrix_mul_t/mod.rs:31-41;  mm dA :63-73)
+//   NN  dX = G.W     (MatrixMatrixMulTBackwardLeft :63-73;  mm forward matrix_matrix_mul/mod.rs:31-41)
+//   TN  dW = G^T.X   (MatrixMatrixMulTBackwardRight :95-105;  mm dB :95-105)
+// A "transposed" operand is never copied: TMA loads it as stored and the UMMA shared-memory
+// descriptor is MN-major instead of K-major.
+//
+// Structure (one CTA per SM, persistent over output tiles):
+//   warp 0      : TMA producer  -- cp.async.bulk.tensor 128B-swizzled boxes into a kStages smem ring
+//   warp 1      : tcgen05.mma issuer (one lane) + TMEM allocation; accumulators 128 x BLOCK_N f32,
+//                 double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2..5  : epilogue -- tcgen05.ld (32 lanes x 32 columns per warp), alpha/beta/bias/ReLU in
+//                 registers, 16-byte global stores
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue).
+#include <stdlib.h>
+
+#include "nk_internal.cuh"
+#include "nk_ptx.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 192;
+constexpr uint32_t kSmemLimit = 232448;  // 227 KB
+
+struct GemmParams {
+  int64_t M, N, K;
+  int64_t ldc;
+  void* C;
+  const void* bias;
+  float alpha, beta;
+  int bias_bf16;
+  int relu;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  // UMMA descriptor parameters (bytes)
+  uint32_t a_lbo, a_sbo, a_kstep;
+  uint32_t b_lbo, b_sbo, b_kstep;
+};
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+  static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int kStagesMax = (kSmemLimit - 2048) / STAGE_BYTES;
+  static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
+  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + 2048;  // + alignment slack + barriers
+  static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                        : (2 * BLOCK_N <= 256) ? 256 : 512;
+};
+
+template <typename TC>
+__device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int64_t row, int64_t col0, const uint32_t* r,
+                                                       int ncols, bool vec_ok) {
+  TC* crow = static_cast<TC*>(p.C) + row * p.ldc + col0;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(r[j]);
+  const bool full = (col0 + 32 <= p.N) && ncols == 32;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < p.N)
+        v[j] += p.bias_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[col0 + j])
+                            : static_cast<const float*>(p.bias)[col0 + j];
+  }
+  if (full && vec_ok) {
+    constexpr int V = 16 / sizeof(TC);
+    if (p.beta != 0.f) {
+#pragma unroll
+      for (int q = 0; q < 32 / V; ++q) {
+        NkVec<TC> c;
+        c.load(crow + q * V);
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[q * V + i] += p.beta * c.get(i);
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 32 / V; ++q) {
+      NkVec<TC> o;
+#pragma unroll
+      for (int i = 0; i < V; ++i) o.set(i, v[q * V + i]);
+      o.store(crow + q * V);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < ncols && col0 + j < p.N) {
+        float x = v[j];
+        if (p.beta != 0.f) x += p.beta * nk_to_f32<TC>(crow[j]);
+        if (p.relu) x = x > 0.f ? x : 0.f;
+        crow[j] = nk_from_f32<TC>(x);
+      }
+    }
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, typename TC>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmParams p) {
+  using C_ = Cfg<BLOCK_N>;
+  constexpr int kStages = C_::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms: 1024 B aligned
+  const uint32_t smem_a0 = smem_base;
+  const uint32_t smem_b0 = smem_base + kStages * C_::A_BYTES;
+  const uint32_t bar_base = smem_base + kStages * C_::STAGE_BYTES;  // 8-byte aligned
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  // generic pointer to the slot, to read the allocated TMEM address back
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tmem_full_bar(s), 1);
+      ptx::mbar_init(tmem_empty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    ptx::tmem_alloc(tmem_slot, C_::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+  if (warp_idx == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m_blocks, n_blk = tile / p.num_m_blocks;
+        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_expect_tx(full_bar(stage), C_::STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          const uint32_t sa = smem_a0 + stage * C_::A_BYTES;
+          const uint32_t sb = smem_b0 + stage * C_::B_BYTES;
+          if (A_MN) {  // stored (K, M): boxes of 64 (m) x 64 (k)
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              ptx::tma_load_2d(sa + c * (64 * BLOCK_K * 2), &tmap_a, full_bar(stage), m0 + c * 64, k0);
+          } else {  // stored (M, K): one box of 64 (k) x 128 (m)
+            ptx::tma_load_2d(sa, &tmap_a, full_bar(stage), k0, m0);
+          }
+          if (B_MN) {  // stored (K, N)
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c)
+              ptx::tma_load_2d(sb + c * (64 * BLOCK_K * 2), &tmap_b, full_bar(stage), n0 + c * 64, k0);
+          } else {  // stored (N, K)
+            ptx::tma_load_2d(sb, &tmap_b, full_bar(stage), k0, n0);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(as * BLOCK_N);
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::make_smem_desc_sw128(smem_a0 + stage * C_::A_BYTES, p.a_lbo, p.a_sbo);
+          const uint64_t bdesc = ptx::make_smem_desc_sw128(smem_b0 + stage * C_::B_BYTES, p.b_lbo, p.b_sbo);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            ptx::mma_f16_ss(tmem_d, adesc + uint64_t((k * p.a_kstep) >> 4), bdesc + uint64_t((k * p.b_kstep) >> 4),
+                            idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::mma_commit(tmem_full_bar(as));  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else {
+    // ===================================================== epilogue (4 warps)
+    const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
+    const bool vec_ok = ((p.ldc * int64_t(sizeof(TC))) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_blocks, n_blk = tile / p.num_m_blocks;
+      const int64_t row = int64_t(m_blk) * BLOCK_M + q * 32 + lane;
+      ptx::mbar_wait(tmem_full_bar(as), aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BLOCK_N);
+      if (BLOCK_N >= 32) {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+          ptx::tmem_ld_wait();
+          const int64_t col0 = int64_t(n_blk) * BLOCK_N + c * 32;
+          if (row < p.M && col0 < p.N) epilogue_store_chunk32<TC>(p, row, col0, r, 32, vec_ok);
+        }
+      } else {
+        uint32_t r[32];
+        uint32_t r16[16];
+        ptx::tmem_ld_32x32b_x16(taddr, r16);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = j < 16 ? r16[j & 15] : 0u;
+        const int64_t col0 = int64_t(n_blk) * BLOCK_N;
+        if (row < p.M && col0 < p.N) epilogue_store_chunk32<TC>(p, row, col0, r, 16, false);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C_::TMEM_COLS);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D bf16 tensor map: `rows` x `cols` row-major with leading dimension ld, box (box_cols=64, box_rows)
+int make_tmap_2d(nk_ctx* ctx, CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                 uint32_t box_cols, uint32_t box_rows) {
+  if (!ctx->encode_tiled) return nk_set_error(ctx, NK_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return nk_set_error(ctx, NK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+                        (long long)rows, (long long)cols, (long long)ld);
+  return NK_OK;
+}
+
+uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* v = getenv(name);
+  return v ? (uint32_t)strtoul(v, nullptr, 0) : dflt;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, typename TC>
+int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p) {
+  using C_ = Cfg<BLOCK_N>;
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, TC>;
+  static bool attr_done = false;  // per template instantiation
+  if (!attr_done) {
+    NK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM_BYTES));
+    attr_done = true;
+  }
+  p.num_n_blocks = int((p.N + BLOCK_N - 1) / BLOCK_N);
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  int grid = num_tiles < ctx->sm_count ? num_tiles : ctx->sm_count;
+  kern<<<grid, kNumThreads, C_::SMEM_BYTES, ctx->stream>>>(ta, tb, p);
+  NK_LAUNCHED(ctx, "gemm_tcgen05");
+  return NK_OK;
+}
+
+template <bool A_MN, bool B_MN, typename TC>
+int launch_bn(nk_ctx* ctx, int block_n, const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p) {
+  switch (block_n) {
+    case 256: return launch_cfg<256, A_MN, B_MN, TC>(ctx, ta, tb, p);
+    case 128: return launch_cfg<128, A_MN, B_MN, TC>(ctx, ta, tb, p);
+    case 64: return launch_cfg<64, A_MN, B_MN, TC>(ctx, ta, tb, p);
+    default:
+      if (!B_MN) {
+        if (block_n == 32) return launch_cfg<32, A_MN, false, TC>(ctx, ta, tb, p);
+        if (block_n == 16) return launch_cfg<16, A_MN, false, TC>(ctx, ta, tb, p);
+      }
+      return nk_set_error(ctx, NK_ERR_UNSUPPORTED, "tcgen05 gemm: unsupported BLOCK_N %d", block_n);
+  }
+}
+
+}  // namespace
+
+bool nk_gemm_tcgen05_supported(int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                               const void* B, int64_t ldb) {
+  (void)transA;
+  (void)transB;
+  if (M <= 0 || N <= 0 || K <= 0) return false;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
+  if ((lda * 2) % 16 != 0 || (ldb * 2) % 16 != 0) return false;  // TMA global strides: multiples of 16 bytes
+  if (M > (int64_t(1) << 30) || N > (int64_t(1) << 30) || K > (int64_t(1) << 30)) return false;
+  return true;
+}
+
+int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
+                    int64_t lda, const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int c_dtype,
+                    const void* bias, int bias_dtype, int relu) {
+  if (!nk_gemm_tcgen05_supported(transA, transB, M, N, K, A, lda, B, ldb)) return NK_ERR_UNSUPPORTED;
+  const bool a_mn = transA != 0;   // op(A) = A^T  -> A stored (K, M), M contiguous
+  const bool b_mn = transB == 0;   // op(B) = B    -> B stored (K, N), N contiguous
+  // tile width: widest that does not leave most of a tile empty
+  int block_n = 256;
+  if (N <= 16 && !b_mn)
+    block_n = 16;
+  else if (N <= 32 && !b_mn)
+    block_n = 32;
+  else if (N <= 64)
+    block_n = 64;
+  else if (N <= 128)
+    block_n = 128;
+  else {
+    // prefer the config with the better wave efficiency on this machine
+    const int64_t mb = (M + BLOCK_M - 1) / BLOCK_M;
+    auto waves_eff = [&](int bn) {
+      int64_t tiles = mb * ((N + bn - 1) / bn);
+      int64_t waves = (tiles + ctx->sm_count - 1) / ctx->sm_count;
+      return double(tiles) / double(waves * ctx->sm_count);
+    };
+    block_n = (waves_eff(128) > waves_eff(256) + 0.08) ? 128 : 256;
+  }
+  block_n = (int)env_u32("NK_GEMM_BLOCK_N", (uint32_t)block_n);
+
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.ldc = ldc;
+  p.C = C;
+  p.bias = bias;
+  p.alpha = alpha;
+  p.beta = beta;
+  p.bias_bf16 = bias_dtype == NK_BF16;
+  p.relu = relu;
+  p.num_m_blocks = int((M + BLOCK_M - 1) / BLOCK_M);
+  p.num_n_blocks = 0;
+  p.num_k_blocks = int((K + BLOCK_K - 1) / BLOCK_K);
+  // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K.  MN-major: 64-wide chunks
+  // BLOCK_K*128 B apart (LBO), 8-k groups 1024 B apart (SBO), +16 rows * 128 B per UMMA_K.
+  p.a_lbo = a_mn ? BLOCK_K * 128 : 16;
+  p.a_sbo = 1024;
+  p.a_kstep = a_mn ? UMMA_K * 128 : UMMA_K * 2;
+  p.b_lbo = b_mn ? BLOCK_K * 128 : 16;
+  p.b_sbo = 1024;
+  p.b_kstep = b_mn ? UMMA_K * 128 : UMMA_K * 2;
+  // debugging overrides (descriptor sweeps on hardware)
+  p.a_lbo = env_u32("NK_DESC_A_LBO", p.a_lbo);
+  p.a_sbo = env_u32("NK_DESC_A_SBO", p.a_sbo);
+  p.b_lbo = env_u32("NK_DESC_B_LBO", p.b_lbo);
+  p.b_sbo = env_u32("NK_DESC_B_SBO", p.b_sbo);
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_mn)
+    rc = make_tmap_2d(ctx, &ta, A, K, M, lda, 64, BLOCK_K);
+  else
+    rc = make_tmap_2d(ctx, &ta, A, M, K, lda, BLOCK_K, BLOCK_M);
+  if (rc) return rc;
+  if (b_mn)
+    rc = make_tmap_2d(ctx, &tb, B, K, N, ldb, 64, BLOCK_K);
+  else
+    rc = make_tmap_2d(ctx, &tb, B, N, K, ldb, BLOCK_K, (uint32_t)block_n);
+  if (rc) return rc;
+
+  static const char* names[2][2][5] = {
+      {{"tcgen05_nt_128x256", "tcgen05_nt_128x128", "tcgen05_nt_128x64", "tcgen05_nt_128x32", "tcgen05_nt_128x16"},
+       {"tcgen05_nn_128x256", "tcgen05_nn_128x128", "tcgen05_nn_128x64", "", ""}},
+      {{"tcgen05_tt_128x256", "tcgen05_tt_128x128", "tcgen05_tt_128x64", "tcgen05_tt_128x32", "tcgen05_tt_128x16"},
+       {"tcgen05_tn_128x256", "tcgen05_tn_128x128", "tcgen05_tn_128x64", "", ""}}};
+  const int bi = block_n == 256 ? 0 : block_n == 128 ? 1 : block_n == 64 ? 2 : block_n == 32 ? 3 : 4;
+  ctx->last_gemm_kernel = names[a_mn][b_mn][bi];
+
+#define NK_TC(AM, BM_)                                                            \
+  (c_dtype == NK_BF16 ? launch_bn<AM, BM_, __nv_bfloat16>(ctx, block_n, ta, tb, p) \
+                      : launch_bn<AM, BM_, float>(ctx, block_n, ta, tb, p))
+  if (!a_mn && !b_mn) return NK_TC(false, false);
+  if (!a_mn && b_mn) return NK_TC(false, true);
+  if (a_mn && !b_mn) return NK_TC(true, false);
+  return NK_TC(true, true);
+#undef NK_TC
+}
+
+extern "C" {
+
+int nk_gemm_bias_act(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha,
+                     const void* A, int64_t lda, const void* B, int64_t ldb, float beta, void* C, int64_t ldc,
+                     int ab_dtype, int c_dtype, const void* bias, int bias_dtype, int relu) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, nk_dtype_ok(ab_dtype) && nk_dtype_ok(c_dtype), "nk_gemm: bad dtype");
+  NK_REQUIRE(ctx, M >= 0 && N >= 0 && K >= 0, "nk_gemm: negative dimension");
+  if (M == 0 || N == 0) return NK_OK;
+  NK_REQUIRE(ctx, C != nullptr && (K == 0 || (A && B)), "nk_gemm: NULL pointer");
+  NK_REQUIRE(ctx, lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N,
+             "nk_gemm: leading dimension too small (lda=%lld ldb=%lld ldc=%lld for M=%lld N=%lld K=%lld tA=%d tB=%d)",
+             (long long)lda, (long long)ldb, (long long)ldc, (long long)M, (long long)N, (long long)K, transA, transB);
+  NK_REQUIRE(ctx, !bias || nk_dtype_ok(bias_dtype), "nk_gemm: bad bias dtype");
+  const bool want_tc = ab_dtype == NK_BF16 && ctx->gemm_engine != NK_GEMM_SIMT && K > 0;
+  if (want_tc) {
+    int rc = nk_gemm_tcgen05(ctx, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, c_dtype, bias,
+                             bias_dtype, relu);
+    if (rc != NK_ERR_UNSUPPORTED) return rc;
+    if (ctx->gemm_engine == NK_GEMM_TCGEN05)
+      return nk_set_error(ctx, NK_ERR_UNSUPPORTED,
+                          "nk_gemm: tcgen05 engine forced but operands are not TMA-addressable "
+                          "(16-byte aligned base, leading dimension multiple of 8 elements)");
+  } else if (ctx->gemm_engine == NK_GEMM_TCGEN05) {
+    return nk_set_error(ctx, NK_ERR_UNSUPPORTED, "nk_gemm: tcgen05 engine forced but operands are not bf16");
+  }
+  return nk_gemm_simt(ctx, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, ab_dtype, c_dtype, bias,
+                      bias_dtype, relu);
+}
+
+int nk_gemm(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
+            int64_t lda, const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype) {
+  return nk_gemm_bias_act(ctx, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, ab_dtype, c_dtype,
+                          nullptr, NK_F32, 0);
+}
+
+}  // extern "C"
