@@ -1,0 +1,95 @@
+/*
+ * nk_graph.h -- C handle API of the host-side graph (C++), the mirror of the reference's
+ * Var / VarDiff op surface over device tensors.
+ *
+ * The reference's host code is Rust (neuronika-variable/src/{var,vardiff,history,gradient}.rs);
+ * no Rust toolchain exists in this environment, so the define-by-run graph above the kernel ABI
+ * (nk_b200.h) is written in C++ (neuronika_b200/csrc/nk_graph.cpp) with the same semantics:
+ *   - a variable is a handle to (data, tape); differentiable variables add (grad, backward tape)
+ *     (var.rs:34-61, vardiff.rs:35-65);
+ *   - op methods only record nodes; nothing is computed until forward() (lazy), which runs every
+ *     node of the tape in creation order (var.rs:110-128); backward(seed) fills the root gradient
+ *     with `seed` and runs the backward nodes in reverse order (vardiff.rs:125-141);
+ *   - every backward node ACCUMULATES into its operands' gradients (beta = 1); leaf gradients
+ *     persist until zero_grad() (vardiff.rs:100-102);
+ *   - differentiability is sticky: Var (x) VarDiff -> VarDiff, and only the needed backward
+ *     halves are built (var.rs:1048-1061).
+ * This header exists so that Python (ctypes) and any other FFI can drive that C++ graph; a Rust
+ * binding would not use it (it would implement Forward/Backward over nk_b200.h directly, see
+ * INTEGRATION.md).
+ *
+ * All functions return 0 or a negative nk_status; nkg_last_error() gives the message (shape
+ * errors carry the reference's own panic text where it has one).
+ */
+#ifndef NK_GRAPH_H
+#define NK_GRAPH_H
+
+#include "nk_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nkg_var nkg_var; /* Var or VarDiff */
+
+typedef enum { NKG_MEAN = 0, NKG_SUM = 1 } nkg_reduction; /* neuronika-variable/src/lib.rs:29-36 */
+
+const char* nkg_last_error(void);
+
+/* ---- leaves (neuronika-variable/src/lib.rs:51-240 constructors; data zero-filled) ---- */
+int nkg_leaf(nk_ctx* ctx, int ndim, const int64_t* shape, int dtype, nkg_var** out);
+/* wrap caller-owned device memory as a leaf (flat parameter / gradient buckets for data parallel) */
+int nkg_leaf_external(nk_ctx* ctx, int ndim, const int64_t* shape, int dtype, void* data_ptr, nkg_var** out);
+/* Var::requires_grad (var.rs:104-107): returns a NEW differentiable handle sharing the data.
+ * grad_dtype < 0 -> same as data; grad_ptr may supply caller-owned gradient storage (or NULL). */
+int nkg_requires_grad(nkg_var* v, int grad_dtype, void* grad_ptr, nkg_var** out);
+int nkg_clone(nkg_var* v, nkg_var** out);
+int nkg_release(nkg_var* v);
+
+/* ---- introspection ---- */
+int nkg_is_diff(nkg_var* v);
+int nkg_ndim(nkg_var* v);
+int nkg_shape(nkg_var* v, int64_t* shape_out);
+int nkg_dtype(nkg_var* v);
+int nkg_grad_dtype(nkg_var* v);
+void* nkg_data_ptr(nkg_var* v);  /* device pointer (allocates the buffer if still lazy) */
+void* nkg_grad_ptr(nkg_var* v);  /* NULL for Var or after no_grad() */
+int nkg_history_len(nkg_var* v); /* number of forward nodes on the tape (test.rs:748-806 checks) */
+int nkg_backward_history_len(nkg_var* v);
+
+/* ---- execution (var.rs:110-128, vardiff.rs:100-165) ---- */
+int nkg_forward(nkg_var* v);
+int nkg_backward(nkg_var* v, float seed);
+int nkg_zero_grad(nkg_var* v);
+int nkg_no_grad(nkg_var* v);
+int nkg_with_grad(nkg_var* v);
+/* host-side peephole fusion over the tape (mm_t + bias add -> one GEMM epilogue, gradient
+ * aliasing through single-consumer adds).  Invisible to results; on by default. */
+int nkg_set_fusion(int enabled);
+
+/* ---- operators (names follow the reference's methods) ---- */
+int nkg_mm(nkg_var* a, nkg_var* b, nkg_var** out);      /* var.rs:1034-1061, vardiff.rs:1073-1106 */
+int nkg_mm_t(nkg_var* a, nkg_var* b, nkg_var** out);    /* var.rs:1065-1094 */
+int nkg_add(nkg_var* a, nkg_var* b, nkg_var** out);     /* vardiff.rs:902-924, broadcasting */
+int nkg_relu(nkg_var* a, nkg_var** out);
+int nkg_softmax(nkg_var* a, int axis, nkg_var** out);
+int nkg_log_softmax(nkg_var* a, int axis, nkg_var** out);
+int nkg_sum(nkg_var* a, nkg_var** out);
+int nkg_mean(nkg_var* a, nkg_var** out);
+int nkg_mse_loss(nkg_var* input, nkg_var* target, int reduction, nkg_var** out);
+int nkg_nll_loss(nkg_var* input, nkg_var* target, int reduction, nkg_var** out);
+int nkg_pad(nkg_var* a, int64_t ph, int64_t pw, float value, nkg_var** out); /* Zero = Constant(0) */
+/* receiver is the KERNEL, argument the input, as in the reference (var.rs:704-716) */
+int nkg_convolution(nkg_var* kernel, nkg_var* input, int64_t sh, int64_t sw, int64_t dh, int64_t dw,
+                    int64_t groups, nkg_var** out);
+/* (N, C, H, W) -> (N, C*H*W): bit-exact view; not in the reference (SURVEY.md 2.2 "missing") */
+int nkg_flatten(nkg_var* a, nkg_var** out);
+
+/* ---- SGD on a leaf (neuronika-optim/src/sgd/mod.rs:191-231) ---- */
+int nkg_sgd_step(nkg_var* param, float* momentum_buf, float* master, float lr, float l2, float momentum,
+                 float dampening, int nesterov, float grad_scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -7,5 +7,8 @@ from . import _lib
 from ._lib import NkError
 from .device import BF16, F32, CuArray, Device
 from . import ops
+from . import variable, nn, optim
+from .variable import (Reduction, Var, VarDiff, from_ndarray, full, ones, rand, set_fusion, zeros)
 
-__all__ = ["Device", "CuArray", "F32", "BF16", "NkError", "ops"]
+__all__ = ["Device", "CuArray", "F32", "BF16", "NkError", "ops", "variable", "nn", "optim", "Var", "VarDiff",
+           "Reduction", "zeros", "ones", "full", "rand", "from_ndarray", "set_fusion"]

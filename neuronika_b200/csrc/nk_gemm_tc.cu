@@ -355,14 +355,10 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   else if (N <= 128)
     block_n = 128;
   else {
-    // prefer the config with the better wave efficiency on this machine
-    const int64_t mb = (M + BLOCK_M - 1) / BLOCK_M;
-    auto waves_eff = [&](int bn) {
-      int64_t tiles = mb * ((N + bn - 1) / bn);
-      int64_t waves = (tiles + ctx->sm_count - 1) / ctx->sm_count;
-      return double(tiles) / double(waves * ctx->sm_count);
-    };
-    block_n = (waves_eff(128) > waves_eff(256) + 0.08) ? 128 : 256;
+    // 128x256 tiles: one MMA reads 16 KB (A) + 32 KB (B) of smem per 512 tensor cycles (96 B/clk, under the
+    // 128 B/clk smem port) -- 128x128 tiles need the full 128 B/clk and measured 938 vs 1342 TFLOP/s at 4096^3
+    // (profiles/r01_gemm_tile_sweep.md), so the wide tile wins even when it quantises worse over 148 SMs.
+    block_n = 256;
   }
   block_n = (int)env_u32("NK_GEMM_BLOCK_N", (uint32_t)block_n);
 

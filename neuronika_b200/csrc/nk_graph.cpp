@@ -1,0 +1,988 @@
+// Host-side define-by-run graph in C++ over the kernel ABI (nk_b200.h): the mirror of the
+// reference's Var / VarDiff / History / Gradient and of its Forward / Backward node structs.
+//
+//   reference (Rust, neuronika-variable/src)                     here
+//   --------------------------------------------------------------------------------------------
+//   Var<D>{data, history}                     var.rs:34-61        Variable{data, fwd tape}
+//   VarDiff<D>{var, grad, history}            vardiff.rs:35-65    Variable{+ grad, bwd tape}
+//   History<T> (BTreeMap in insertion order)  history.rs:54-124   std::map<op id, node> + buffer
+//   Gradient<T,D> (RefCell<Option<array>>)    gradient.rs:14-79   Gradient (lazy device buffer)
+//   trait Forward / trait Backward            autograd.rs:7-25    struct Forward / struct Backward
+//   node structs (one Forward + 1..3 Backward per op)  node/*/mod.rs   classes of the same names
+//
+// Protocol kept bit-for-bit: op methods only record nodes; forward() recomputes the whole tape in
+// creation order; backward(seed) fills the root gradient and runs the backward tape in reverse;
+// every Backward accumulates into its operand gradients.  Two host-side optimisations are
+// invisible to results: (1) buffers are allocated lazily and a gradient known to be all-zero is
+// overwritten (beta = 0) instead of read-modify-written; (2) a peephole over the tape fuses
+// mm_t + bias-add into one GEMM epilogue and aliases the gradient of a single-consumer addend.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "nk_graph.h"
+
+namespace nkg {
+
+static thread_local std::string g_error;
+static bool g_fusion = true;
+static uint64_t g_next_op_id = 1;  // creation order == a topological order (history.rs:84-88)
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] static void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  throw Error(code, buf);
+}
+
+static inline void ck(nk_ctx* ctx, int rc) {
+  if (rc != NK_OK) throw Error(rc, nk_last_error(ctx));
+}
+
+using Shape = std::vector<int64_t>;
+static int64_t numel(const Shape& s) {
+  int64_t n = 1;
+  for (auto d : s) n *= d;
+  return n;
+}
+static size_t esize(int dt) { return dt == NK_BF16 ? 2 : 4; }
+
+// ------------------------------------------------------------------------------- Tensor
+struct Tensor {
+  nk_ctx* ctx;
+  Shape shape;
+  int dtype;
+  void* ptr = nullptr;
+  bool owned = true;
+  std::shared_ptr<Tensor> base;  // view of another tensor (flatten)
+  Tensor(nk_ctx* c, Shape s, int dt) : ctx(c), shape(std::move(s)), dtype(dt) {}
+  ~Tensor() {
+    if (owned && ptr && !base) nk_free(ctx, ptr);
+  }
+  int64_t n() const { return numel(shape); }
+  // buffer about to be fully overwritten: no zero fill needed
+  void* wptr() {
+    if (base) return base->wptr();
+    if (!ptr) {
+      ck(ctx, nk_alloc(ctx, size_t(n()) * esize(dtype), &ptr));  // nk_alloc zero-fills (CuArray::zeroed)
+    }
+    return ptr;
+  }
+  void* rptr() { return wptr(); }
+};
+using TensorP = std::shared_ptr<Tensor>;
+
+// ------------------------------------------------------------------------------- Gradient
+struct Gradient {
+  nk_ctx* ctx;
+  Shape shape;
+  int dtype;
+  void* ptr = nullptr;
+  bool owned = true;
+  bool enabled = true;   // false after no_grad()
+  bool is_zero = true;   // content known to be all zeros -> first accumulate may overwrite
+  std::shared_ptr<Gradient> alias;  // fusion: this gradient IS that gradient
+  Gradient(nk_ctx* c, Shape s, int dt) : ctx(c), shape(std::move(s)), dtype(dt) {}
+  ~Gradient() {
+    if (owned && ptr) nk_free(ctx, ptr);
+  }
+  Gradient* root() { return alias ? alias->root() : this; }
+  int64_t n() const { return numel(shape); }
+  void* get() {
+    Gradient* r = root();
+    if (!r->enabled)
+      fail(NK_ERR_INVALID_ARG,
+           "Trying to get a de-allocated gradient. Switch on the gradients first by using `.with_grad()`");
+    if (!r->ptr) {
+      ck(r->ctx, nk_alloc(r->ctx, size_t(r->n()) * esize(r->dtype), &r->ptr));
+      r->is_zero = true;
+    }
+    return r->ptr;
+  }
+  // beta for an accumulating write (0 when known zero), and mark the buffer as touched
+  float acc_beta() {
+    Gradient* r = root();
+    float b = r->is_zero ? 0.f : 1.f;
+    r->is_zero = false;
+    return b;
+  }
+  void zero() {
+    Gradient* r = root();
+    if (r->ptr && !r->is_zero) ck(r->ctx, nk_memset0(r->ctx, r->ptr, size_t(r->n()) * esize(r->dtype)));
+    r->is_zero = true;
+  }
+  void fill(float v) {
+    Gradient* r = root();
+    ck(r->ctx, nk_fill(r->ctx, get(), r->dtype, size_t(r->n()), v));
+    r->is_zero = false;
+  }
+  void no_grad() {  // gradient.rs:68-71
+    Gradient* r = root();
+    if (r->owned && r->ptr) nk_free(r->ctx, r->ptr);
+    if (r->owned) r->ptr = nullptr;
+    r->enabled = false;
+  }
+  void with_grad() {  // gradient.rs:73-78 (fresh zeros)
+    Gradient* r = root();
+    if (!r->enabled) {
+      r->enabled = true;
+      r->is_zero = true;
+      if (!r->owned && r->ptr) ck(r->ctx, nk_memset0(r->ctx, r->ptr, size_t(r->n()) * esize(r->dtype)));
+    }
+  }
+};
+using GradientP = std::shared_ptr<Gradient>;
+
+// ------------------------------------------------------------------------------- node traits
+struct Forward {
+  bool skip = false;  // fused into a consumer
+  virtual ~Forward() {}
+  virtual void forward() = 0;
+  virtual const char* name() const = 0;
+};
+struct Backward {
+  GradientP gradient;  // gradient of this node's output
+  bool skip = false;
+  virtual ~Backward() {}
+  virtual void backward() = 0;
+  virtual const char* name() const = 0;
+  virtual void no_grad() {
+    if (gradient) gradient->no_grad();
+  }
+  virtual void with_grad() {
+    if (gradient) gradient->with_grad();
+  }
+};
+using ForwardP = std::shared_ptr<Forward>;
+using BackwardP = std::shared_ptr<Backward>;
+
+static void gemm(nk_ctx* ctx, bool ta, bool tb, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                 const void* B, int64_t ldb, float beta, void* C, int ab_dt, int c_dt, const void* bias = nullptr,
+                 int bias_dt = NK_F32, int relu = 0) {
+  ck(ctx, nk_gemm_bias_act(ctx, ta, tb, M, N, K, 1.f, A, lda, B, ldb, beta, C, N, ab_dt, c_dt, bias, bias_dt, relu));
+}
+
+// ------------------------------------------------------------------------------- matmul nodes
+// MatrixMatrixMul (matrix_matrix_mul/mod.rs:11-41) and MatrixMatrixMulT (matrix_matrix_mul_t/mod.rs:11-41)
+struct MatMul : Forward {
+  nk_ctx* ctx;
+  TensorP left, right, data;
+  bool t;  // true: C = A.B^T (mm_t)
+  MatMul(nk_ctx* c, TensorP l, TensorP r, TensorP d, bool tt) : ctx(c), left(l), right(r), data(d), t(tt) {}
+  const char* name() const override { return t ? "MatrixMatrixMulT" : "MatrixMatrixMul"; }
+  void forward() override { run(nullptr); }
+  void run(Tensor* bias, Tensor* out = nullptr) {
+    Tensor* o = out ? out : data.get();
+    const int64_t M = left->shape[0], K = left->shape[1], N = t ? right->shape[0] : right->shape[1];
+    gemm(ctx, false, t, M, N, K, left->rptr(), left->shape[1], right->rptr(), right->shape[1], 0.f, o->wptr(),
+         left->dtype, o->dtype, bias ? bias->rptr() : nullptr, bias ? bias->dtype : NK_F32, 0);
+  }
+};
+
+// dA += G.B^T | G.B ; dB += A^T.G | G^T.A   (matrix_matrix_mul/mod.rs:43-126, matrix_matrix_mul_t/mod.rs:43-126)
+struct MatMulBackward : Backward {
+  nk_ctx* ctx;
+  TensorP left_data, right_data;
+  GradientP left_grad, right_grad;  // either may be null (operand not differentiable)
+  bool t;
+  const char* name() const override { return t ? "MatrixMatrixMulTBackward" : "MatrixMatrixMulBackward"; }
+  void backward() override {
+    const int64_t M = left_data->shape[0], K = left_data->shape[1];
+    const int64_t N = t ? right_data->shape[0] : right_data->shape[1];
+    const void* G = gradient->get();
+    const int gdt = gradient->dtype;
+    if (left_grad) {  // (M,K)
+      void* d = left_grad->get();
+      float beta = left_grad->acc_beta();
+      if (t)  // dX += G.W      : (M,N).(N,K)   NN
+        gemm(ctx, false, false, M, K, N, G, N, right_data->rptr(), K, beta, d, gdt, left_grad->dtype);
+      else    // dA += G.B^T    : (M,N).(K,N)^T NT
+        gemm(ctx, false, true, M, K, N, G, N, right_data->rptr(), N, beta, d, gdt, left_grad->dtype);
+    }
+    if (right_grad) {
+      void* d = right_grad->get();
+      float beta = right_grad->acc_beta();
+      if (t)  // dW += G^T.X    : (M,N)^T.(M,K) -> (N,K)  TN
+        gemm(ctx, true, false, N, K, M, G, N, left_data->rptr(), K, beta, d, gdt, right_grad->dtype);
+      else    // dB += A^T.G    : (M,K)^T.(M,N) -> (K,N)  TN
+        gemm(ctx, true, false, K, N, M, left_data->rptr(), K, G, N, beta, d, gdt, right_grad->dtype);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------- addition
+struct Addition : Forward {  // addition/mod.rs:11-50
+  nk_ctx* ctx;
+  TensorP left, right, data;
+  std::shared_ptr<MatMul> fused_gemm;  // peephole: data = mm_t(..) + right in one kernel
+  const char* name() const override { return "Addition"; }
+  void forward() override {
+    if (fused_gemm) {
+      fused_gemm->run(right.get(), data.get());
+      return;
+    }
+    ck(ctx, nk_add_bcast_fwd(ctx, data->wptr(), left->rptr(), right->rptr(), data->dtype, (int)data->shape.size(),
+                             data->shape.data(), (int)left->shape.size(), left->shape.data(),
+                             (int)right->shape.size(), right->shape.data()));
+  }
+};
+
+struct AdditionBackward : Backward {  // addition/mod.rs:52-135 (Left, Right and the composite)
+  nk_ctx* ctx;
+  GradientP left_grad, right_grad;
+  bool left_aliased = false, right_aliased = false;
+  const char* name() const override { return "AdditionBackward"; }
+  void acc(GradientP& dst, bool aliased) {
+    if (!dst || aliased) return;
+    void* d = dst->get();
+    float beta = dst->acc_beta();
+    ck(ctx, nk_unbroadcast_acc(ctx, d, dst->dtype, (int)dst->shape.size(), dst->shape.data(), gradient->get(),
+                               gradient->dtype, (int)gradient->shape.size(), gradient->shape.data(), beta));
+  }
+  void backward() override {
+    acc(left_grad, left_aliased);
+    acc(right_grad, right_aliased);
+  }
+};
+
+// ------------------------------------------------------------------------------- unary / softmax
+struct ReLU : Forward {  // relu/mod.rs:11-38
+  nk_ctx* ctx;
+  TensorP operand, data;
+  const char* name() const override { return "ReLU"; }
+  void forward() override {
+    ck(ctx, nk_relu_fwd(ctx, data->wptr(), operand->rptr(), size_t(data->n()), data->dtype));
+  }
+};
+struct ReLUBackward : Backward {  // relu/mod.rs:40-79
+  nk_ctx* ctx;
+  TensorP operand_data;
+  GradientP operand_grad;
+  const char* name() const override { return "ReLUBackward"; }
+  void backward() override {
+    void* d = operand_grad->get();
+    float beta = operand_grad->acc_beta();
+    ck(ctx, nk_relu_bwd(ctx, d, operand_data->rptr(), gradient->get(), size_t(operand_data->n()),
+                        operand_data->dtype, beta));
+  }
+};
+
+static void lanes(const Shape& s, int axis, int64_t& outer, int64_t& len, int64_t& inner) {
+  outer = inner = 1;
+  for (int i = 0; i < axis; ++i) outer *= s[i];
+  len = s[axis];
+  for (size_t i = axis + 1; i < s.size(); ++i) inner *= s[i];
+}
+
+struct Softmax : Forward {  // softmax/mod.rs:11-53, logsoftmax/mod.rs:11-53
+  nk_ctx* ctx;
+  TensorP operand, data;
+  int axis;
+  bool log;
+  const char* name() const override { return log ? "LogSoftmax" : "Softmax"; }
+  void forward() override {
+    int64_t o, l, i;
+    lanes(data->shape, axis, o, l, i);
+    ck(ctx, (log ? nk_log_softmax_fwd : nk_softmax_fwd)(ctx, data->wptr(), operand->rptr(), o, l, i, data->dtype));
+  }
+};
+struct SoftmaxBackward : Backward {  // softmax/mod.rs:55-104, logsoftmax/mod.rs:55-102
+  nk_ctx* ctx;
+  TensorP data;
+  GradientP operand_grad;
+  int axis;
+  bool log;
+  const char* name() const override { return log ? "LogSoftmaxBackward" : "SoftmaxBackward"; }
+  void backward() override {
+    int64_t o, l, i;
+    lanes(data->shape, axis, o, l, i);
+    void* d = operand_grad->get();
+    float beta = operand_grad->acc_beta();
+    ck(ctx, (log ? nk_log_softmax_bwd : nk_softmax_bwd)(ctx, d, data->rptr(), gradient->get(), o, l, i, data->dtype,
+                                                         beta));
+  }
+};
+
+// ------------------------------------------------------------------------------- reductions / losses
+struct SumMean : Forward {  // sum/mod.rs:11-34, mean/mod.rs:11-34
+  nk_ctx* ctx;
+  TensorP operand, data;
+  bool mean;
+  const char* name() const override { return mean ? "Mean" : "Sum"; }
+  void forward() override {
+    ck(ctx, nk_sum_fwd(ctx, (float*)data->wptr(), operand->rptr(), size_t(operand->n()), operand->dtype, mean));
+  }
+};
+struct SumMeanBackward : Backward {  // sum/mod.rs:36-66, mean/mod.rs:36-71
+  nk_ctx* ctx;
+  GradientP operand_grad;
+  bool mean;
+  const char* name() const override { return mean ? "MeanBackward" : "SumBackward"; }
+  void backward() override {
+    void* d = operand_grad->get();
+    float beta = operand_grad->acc_beta();
+    ck(ctx, nk_sum_bwd(ctx, d, (const float*)gradient->get(), size_t(operand_grad->n()), operand_grad->dtype, mean,
+                       beta));
+  }
+};
+
+struct Loss : Forward {  // squared_error/mod.rs:11-58, nll/mod.rs:11-68
+  nk_ctx* ctx;
+  TensorP input, target, data;
+  bool mean, nll;
+  const char* name() const override { return nll ? "NegativeLogLikelihood" : "SquaredError"; }
+  void forward() override {
+    if (nll)
+      ck(ctx, nk_nll_fwd(ctx, (float*)data->wptr(), input->rptr(), target->rptr(), input->shape[0], input->shape[1],
+                         input->dtype, mean));
+    else
+      ck(ctx, nk_mse_fwd(ctx, (float*)data->wptr(), input->rptr(), target->rptr(), size_t(input->n()), input->dtype,
+                         mean));
+  }
+};
+struct LossBackward : Backward {  // squared_error/mod.rs:60-122, nll/mod.rs:70-133
+  nk_ctx* ctx;
+  TensorP input, target;
+  GradientP input_grad;
+  bool mean, nll;
+  const char* name() const override { return nll ? "NegativeLogLikelihoodBackward" : "SquaredErrorBackward"; }
+  void backward() override {
+    void* d = input_grad->get();
+    float beta = input_grad->acc_beta();
+    const float* g = (const float*)gradient->get();
+    if (nll)
+      ck(ctx, nk_nll_bwd(ctx, d, target->rptr(), g, input->shape[0], input->shape[1], input->dtype, mean, beta));
+    else
+      ck(ctx, nk_mse_bwd(ctx, d, input->rptr(), target->rptr(), g, size_t(input->n()), input->dtype, mean, beta));
+  }
+};
+
+// ------------------------------------------------------------------------------- pad / conv / flatten
+struct Pad : Forward {  // pad/mod.rs:63-129 with Constant / Zero modes
+  nk_ctx* ctx;
+  TensorP operand, data;
+  int64_t ph, pw;
+  float value;
+  const char* name() const override { return "Pad"; }
+  void forward() override {
+    const Shape& s = operand->shape;
+    ck(ctx, nk_pad2d_fwd(ctx, data->wptr(), operand->rptr(), s[0] * s[1], s[2], s[3], ph, pw, value, data->dtype));
+  }
+};
+struct PadBackward : Backward {  // pad/mod.rs:131-182
+  nk_ctx* ctx;
+  GradientP operand_grad;
+  int64_t ph, pw;
+  const char* name() const override { return "PadBackward"; }
+  void backward() override {
+    const Shape& s = operand_grad->shape;
+    void* d = operand_grad->get();
+    float beta = operand_grad->acc_beta();
+    ck(ctx, nk_pad2d_bwd(ctx, d, gradient->get(), s[0] * s[1], s[2], s[3], ph, pw, operand_grad->dtype, beta));
+  }
+};
+
+struct ConvArgs {
+  int64_t n, cin, h, w, cout, kh, kw, sh, sw, dh, dw, groups;
+};
+struct Convolution : Forward {  // convolution/mod.rs:296-355
+  nk_ctx* ctx;
+  TensorP input, kernel, data;
+  ConvArgs a;
+  const char* name() const override { return "Convolution"; }
+  void forward() override {
+    ck(ctx, nk_conv2d_fwd(ctx, data->wptr(), input->rptr(), kernel->rptr(), nullptr, 0, a.n, a.cin, a.h, a.w, a.cout,
+                          a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups, data->dtype));
+  }
+};
+struct ConvolutionBackward : Backward {  // convolution/mod.rs:357-510: input first, then kernel (:380-388)
+  nk_ctx* ctx;
+  TensorP input, kernel;
+  GradientP input_grad, kernel_grad;
+  ConvArgs a;
+  const char* name() const override { return "ConvolutionBackward"; }
+  void backward() override {
+    if (input_grad) {
+      void* d = input_grad->get();
+      float beta = input_grad->acc_beta();
+      ck(ctx, nk_conv2d_bwd_input(ctx, d, gradient->get(), kernel->rptr(), a.n, a.cin, a.h, a.w, a.cout, a.kh, a.kw,
+                                  a.sh, a.sw, a.dh, a.dw, a.groups, gradient->dtype, beta));
+    }
+    if (kernel_grad) {
+      void* d = kernel_grad->get();
+      float beta = kernel_grad->acc_beta();
+      ck(ctx, nk_conv2d_bwd_kernel(ctx, d, kernel_grad->dtype, nullptr, gradient->get(), input->rptr(), a.n, a.cin,
+                                   a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups, gradient->dtype,
+                                   beta));
+    }
+  }
+};
+
+}  // namespace nkg
+
+// ------------------------------------------------------------------------------- Variable (handle)
+using namespace nkg;
+
+struct nkg_var {
+  nk_ctx* ctx = nullptr;
+  TensorP data;
+  std::map<uint64_t, ForwardP> fwd;  // History<(Rc<dyn Forward>, Cell<bool>)>
+  std::vector<ForwardP> fwd_buf;
+  GradientP grad;                    // null => Var
+  std::map<uint64_t, BackwardP> bwd; // History<(Rc<dyn Backward>, Rc<dyn NoGrad>)>
+  std::vector<BackwardP> bwd_buf;
+  bool diff() const { return grad != nullptr; }
+};
+
+namespace {
+
+nkg_var* new_like(nkg_var* a) {
+  nkg_var* v = new nkg_var();
+  v->ctx = a->ctx;
+  return v;
+}
+
+void merge(nkg_var* dst, const nkg_var* a, const nkg_var* b = nullptr) {  // History::merge
+  dst->fwd = a->fwd;
+  dst->bwd = a->bwd;
+  if (b) {
+    dst->fwd.insert(b->fwd.begin(), b->fwd.end());
+    dst->bwd.insert(b->bwd.begin(), b->bwd.end());
+  }
+}
+
+uint64_t push(nkg_var* v, ForwardP op) {
+  uint64_t id = g_next_op_id++;
+  v->fwd[id] = std::move(op);
+  return id;
+}
+void push_bwd(nkg_var* v, uint64_t id, BackwardP op) { v->bwd[id] = std::move(op); }
+
+void require_same_dtype(nkg_var* a, nkg_var* b, const char* who) {
+  if (a->data->dtype != b->data->dtype) fail(NK_ERR_INVALID_ARG, "%s: operands have different element types", who);
+  if (a->ctx != b->ctx) fail(NK_ERR_INVALID_ARG, "%s: operands live on different devices", who);
+}
+
+Shape cobroadcast(const Shape& l, const Shape& r) {  // utils.rs:97-125
+  const Shape& big = l.size() >= r.size() ? l : r;
+  const Shape& small = l.size() >= r.size() ? r : l;
+  Shape out = big;
+  size_t off = big.size() - small.size();
+  for (size_t i = 0; i < small.size(); ++i) {
+    int64_t& o = out[off + i];
+    if (o != small[i]) {
+      if (o == 1)
+        o = small[i];
+      else if (small[i] != 1)
+        fail(NK_ERR_INVALID_ARG, "The two tensors have incompatible shape.");
+    }
+  }
+  return out;
+}
+
+// ---- peephole fusion, run when the tapes are materialised by forward()
+void fuse(nkg_var* v) {
+  if (!g_fusion) return;
+  // producer lookup: output tensor -> MatMul op
+  std::map<Tensor*, std::shared_ptr<MatMul>> producers;
+  for (auto& kv : v->fwd)
+    if (auto mm = std::dynamic_pointer_cast<MatMul>(kv.second)) producers[mm->data.get()] = mm;
+  for (auto& kv : v->fwd) {
+    auto add = std::dynamic_pointer_cast<Addition>(kv.second);
+    if (!add || add->fused_gemm) continue;
+    auto it = producers.find(add->left.get());
+    if (it == producers.end()) continue;
+    auto mm = it->second;
+    // bias must be a (N) row broadcast of the (M,N) product, same element type; the product must have no
+    // other holder than its producer and this consumer (no live variable handle, no second consumer)
+    const Shape& os = add->data->shape;
+    if (!mm->t || os.size() != 2 || add->right->shape.size() != 1 || add->right->shape[0] != os[1]) continue;
+    if (add->right->dtype != add->data->dtype || add->left->shape != os) continue;
+    if (add->left.use_count() != 2) continue;
+    add->fused_gemm = mm;
+    mm->skip = true;
+  }
+  // gradient aliasing: dL += G with identical shape/dtype and a single consumer => L.grad is G
+  for (auto& kv : v->bwd) {
+    auto ab = std::dynamic_pointer_cast<AdditionBackward>(kv.second);
+    if (!ab) continue;
+    auto try_alias = [&](GradientP& g, bool& flag) {
+      if (!g || flag || g->alias || g->ptr) return;
+      if (g->shape != ab->gradient->shape || g->dtype != ab->gradient->dtype) return;
+      if (!g->owned) return;
+      if (g.use_count() != 2) return;  // the producer's Backward node + this node
+      g->alias = ab->gradient;
+      flag = true;
+    };
+    try_alias(ab->left_grad, ab->left_aliased);
+  }
+}
+
+void materialise(nkg_var* v) {
+  if (v->fwd_buf.size() != v->fwd.size()) {
+    fuse(v);
+    v->fwd_buf.clear();
+    for (auto& kv : v->fwd) v->fwd_buf.push_back(kv.second);
+  }
+  if (v->bwd_buf.size() != v->bwd.size()) {
+    v->bwd_buf.clear();
+    for (auto& kv : v->bwd) v->bwd_buf.push_back(kv.second);
+  }
+}
+
+template <typename F>
+int guard(F&& f) {
+  try {
+    f();
+    return NK_OK;
+  } catch (const Error& e) {
+    g_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return NK_ERR_INVALID_ARG;
+  }
+}
+
+nkg_var* unary_node(nkg_var* a, const Shape& out_shape, int out_dtype, TensorP& out_data) {
+  nkg_var* v = new_like(a);
+  merge(v, a);
+  out_data = std::make_shared<Tensor>(a->ctx, out_shape, out_dtype);
+  v->data = out_data;
+  return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* nkg_last_error(void) { return g_error.c_str(); }
+
+int nkg_set_fusion(int enabled) {
+  g_fusion = enabled != 0;
+  return NK_OK;
+}
+
+int nkg_leaf(nk_ctx* ctx, int ndim, const int64_t* shape, int dtype, nkg_var** out) {
+  return guard([&] {
+    if (!ctx || !out || ndim < 0 || ndim > NK_MAX_DIMS) fail(NK_ERR_INVALID_ARG, "nkg_leaf: bad arguments");
+    if (dtype != NK_F32 && dtype != NK_BF16) fail(NK_ERR_INVALID_ARG, "nkg_leaf: bad dtype %d", dtype);
+    nkg_var* v = new nkg_var();
+    v->ctx = ctx;
+    v->data = std::make_shared<Tensor>(ctx, Shape(shape, shape + ndim), dtype);
+    v->data->wptr();  // leaves are allocated (zero-filled) eagerly
+    *out = v;
+  });
+}
+
+int nkg_leaf_external(nk_ctx* ctx, int ndim, const int64_t* shape, int dtype, void* data_ptr, nkg_var** out) {
+  return guard([&] {
+    if (!ctx || !out || !data_ptr || ndim < 0 || ndim > NK_MAX_DIMS)
+      fail(NK_ERR_INVALID_ARG, "nkg_leaf_external: bad arguments");
+    nkg_var* v = new nkg_var();
+    v->ctx = ctx;
+    v->data = std::make_shared<Tensor>(ctx, Shape(shape, shape + ndim), dtype);
+    v->data->ptr = data_ptr;
+    v->data->owned = false;
+    *out = v;
+  });
+}
+
+int nkg_requires_grad(nkg_var* a, int grad_dtype, void* grad_ptr, nkg_var** out) {
+  return guard([&] {
+    if (!a || !out) fail(NK_ERR_INVALID_ARG, "nkg_requires_grad: NULL");
+    nkg_var* v = new nkg_var(*a);  // shares data and forward tape (VarDiff::leaf(self, zeros))
+    v->grad = std::make_shared<Gradient>(a->ctx, a->data->shape, grad_dtype < 0 ? a->data->dtype : grad_dtype);
+    if (grad_ptr) {
+      v->grad->ptr = grad_ptr;
+      v->grad->owned = false;
+      v->grad->is_zero = false;  // caller-owned memory: contents unknown
+    }
+    v->bwd.clear();
+    v->bwd_buf.clear();
+    *out = v;
+  });
+}
+
+int nkg_clone(nkg_var* a, nkg_var** out) {
+  return guard([&] {
+    if (!a || !out) fail(NK_ERR_INVALID_ARG, "nkg_clone: NULL");
+    *out = new nkg_var(*a);
+  });
+}
+
+int nkg_release(nkg_var* v) {
+  delete v;
+  return NK_OK;
+}
+
+int nkg_is_diff(nkg_var* v) { return v && v->diff(); }
+int nkg_ndim(nkg_var* v) { return v ? (int)v->data->shape.size() : -1; }
+int nkg_shape(nkg_var* v, int64_t* s) {
+  if (!v || !s) return NK_ERR_INVALID_ARG;
+  for (size_t i = 0; i < v->data->shape.size(); ++i) s[i] = v->data->shape[i];
+  return NK_OK;
+}
+int nkg_dtype(nkg_var* v) { return v ? v->data->dtype : -1; }
+int nkg_grad_dtype(nkg_var* v) { return v && v->grad ? v->grad->dtype : -1; }
+void* nkg_data_ptr(nkg_var* v) {
+  void* p = nullptr;
+  guard([&] { p = v ? v->data->rptr() : nullptr; });
+  return p;
+}
+void* nkg_grad_ptr(nkg_var* v) {
+  void* p = nullptr;
+  guard([&] {
+    if (v && v->grad && v->grad->root()->enabled) p = v->grad->get();
+  });
+  return p;
+}
+int nkg_history_len(nkg_var* v) { return v ? (int)v->fwd.size() : -1; }
+int nkg_backward_history_len(nkg_var* v) { return v ? (int)v->bwd.size() : -1; }
+
+int nkg_forward(nkg_var* v) {
+  return guard([&] {
+    if (!v) fail(NK_ERR_INVALID_ARG, "nkg_forward: NULL");
+    materialise(v);
+    for (auto& op : v->fwd_buf)
+      if (!op->skip) op->forward();
+  });
+}
+
+int nkg_backward(nkg_var* v, float seed) {
+  return guard([&] {
+    if (!v || !v->diff()) fail(NK_ERR_INVALID_ARG, "nkg_backward: not a differentiable variable");
+    if (v->fwd_buf.size() != v->fwd.size() || v->bwd_buf.size() != v->bwd.size())
+      fail(NK_ERR_INVALID_ARG, "Perhaps you forgot to call .forward()?");  // vardiff.rs:126-130
+    v->grad->fill(seed);
+    for (auto it = v->bwd_buf.rbegin(); it != v->bwd_buf.rend(); ++it)
+      if (!(*it)->skip) (*it)->backward();
+  });
+}
+
+int nkg_zero_grad(nkg_var* v) {
+  return guard([&] {
+    if (!v || !v->diff()) fail(NK_ERR_INVALID_ARG, "nkg_zero_grad: not a differentiable variable");
+    v->grad->get();
+    v->grad->zero();
+  });
+}
+
+int nkg_no_grad(nkg_var* v) {
+  return guard([&] {
+    if (!v || !v->diff()) fail(NK_ERR_INVALID_ARG, "nkg_no_grad: not a differentiable variable");
+    materialise(v);
+    for (auto& op : v->bwd_buf) op->no_grad();
+  });
+}
+
+int nkg_with_grad(nkg_var* v) {
+  return guard([&] {
+    if (!v || !v->diff()) fail(NK_ERR_INVALID_ARG, "nkg_with_grad: not a differentiable variable");
+    materialise(v);
+    for (auto& op : v->bwd_buf) op->with_grad();
+  });
+}
+
+// ---------------------------------------------------------------- operators
+static int matmul_impl(nkg_var* a, nkg_var* b, bool t, nkg_var** out) {
+  return guard([&] {
+    if (!a || !b || !out) fail(NK_ERR_INVALID_ARG, "mm: NULL");
+    require_same_dtype(a, b, t ? "mm_t" : "mm");
+    const Shape &ls = a->data->shape, &rs = b->data->shape;
+    if (ls.size() != 2 || rs.size() != 2) fail(NK_ERR_INVALID_ARG, "mm: operands must be 2-dimensional");
+    const int64_t inner_r = t ? rs[1] : rs[0];
+    if (ls[1] != inner_r)
+      fail(NK_ERR_INVALID_ARG, "mm: incompatible shapes (%lld, %lld) and (%lld, %lld)%s", (long long)ls[0],
+           (long long)ls[1], (long long)rs[0], (long long)rs[1], t ? " (transposed rhs)" : "");
+    nkg_var* v = new_like(a);
+    merge(v, a, b);
+    Shape os{ls[0], t ? rs[0] : rs[1]};
+    v->data = std::make_shared<Tensor>(a->ctx, os, a->data->dtype);
+    uint64_t id = push(v, std::make_shared<MatMul>(a->ctx, a->data, b->data, v->data, t));
+    if (a->diff() || b->diff()) {
+      v->grad = std::make_shared<Gradient>(a->ctx, os, a->data->dtype);
+      auto bw = std::make_shared<MatMulBackward>();
+      bw->ctx = a->ctx;
+      bw->t = t;
+      bw->gradient = v->grad;
+      bw->left_data = a->data;
+      bw->right_data = b->data;
+      bw->left_grad = a->grad;   // null when the operand is a Var: that half is never built
+      bw->right_grad = b->grad;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+
+int nkg_mm(nkg_var* a, nkg_var* b, nkg_var** out) { return matmul_impl(a, b, false, out); }
+int nkg_mm_t(nkg_var* a, nkg_var* b, nkg_var** out) { return matmul_impl(a, b, true, out); }
+
+int nkg_add(nkg_var* a, nkg_var* b, nkg_var** out) {
+  return guard([&] {
+    if (!a || !b || !out) fail(NK_ERR_INVALID_ARG, "add: NULL");
+    require_same_dtype(a, b, "add");
+    Shape os = cobroadcast(a->data->shape, b->data->shape);
+    nkg_var* v = new_like(a);
+    merge(v, a, b);
+    v->data = std::make_shared<Tensor>(a->ctx, os, a->data->dtype);
+    auto op = std::make_shared<Addition>();
+    op->ctx = a->ctx;
+    op->left = a->data;
+    op->right = b->data;
+    op->data = v->data;
+    uint64_t id = push(v, op);
+    if (a->diff() || b->diff()) {
+      v->grad = std::make_shared<Gradient>(a->ctx, os, a->data->dtype);
+      auto bw = std::make_shared<AdditionBackward>();
+      bw->ctx = a->ctx;
+      bw->gradient = v->grad;
+      bw->left_grad = a->grad;
+      bw->right_grad = b->grad;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+
+int nkg_relu(nkg_var* a, nkg_var** out) {
+  return guard([&] {
+    if (!a || !out) fail(NK_ERR_INVALID_ARG, "relu: NULL");
+    TensorP od;
+    nkg_var* v = unary_node(a, a->data->shape, a->data->dtype, od);
+    auto op = std::make_shared<ReLU>();
+    op->ctx = a->ctx;
+    op->operand = a->data;
+    op->data = od;
+    uint64_t id = push(v, op);
+    if (a->diff()) {
+      v->grad = std::make_shared<Gradient>(a->ctx, od->shape, od->dtype);
+      auto bw = std::make_shared<ReLUBackward>();
+      bw->ctx = a->ctx;
+      bw->gradient = v->grad;
+      bw->operand_data = a->data;
+      bw->operand_grad = a->grad;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+
+static int softmax_impl(nkg_var* a, int axis, bool log, nkg_var** out) {
+  return guard([&] {
+    if (!a || !out) fail(NK_ERR_INVALID_ARG, "softmax: NULL");
+    if (axis < 0 || axis >= (int)a->data->shape.size()) fail(NK_ERR_INVALID_ARG, "softmax: axis %d out of range", axis);
+    TensorP od;
+    nkg_var* v = unary_node(a, a->data->shape, a->data->dtype, od);
+    auto op = std::make_shared<Softmax>();
+    op->ctx = a->ctx;
+    op->operand = a->data;
+    op->data = od;
+    op->axis = axis;
+    op->log = log;
+    uint64_t id = push(v, op);
+    if (a->diff()) {
+      v->grad = std::make_shared<Gradient>(a->ctx, od->shape, od->dtype);
+      auto bw = std::make_shared<SoftmaxBackward>();
+      bw->ctx = a->ctx;
+      bw->gradient = v->grad;
+      bw->data = od;
+      bw->operand_grad = a->grad;
+      bw->axis = axis;
+      bw->log = log;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+int nkg_softmax(nkg_var* a, int axis, nkg_var** out) { return softmax_impl(a, axis, false, out); }
+int nkg_log_softmax(nkg_var* a, int axis, nkg_var** out) { return softmax_impl(a, axis, true, out); }
+
+static int summean_impl(nkg_var* a, bool mean, nkg_var** out) {
+  return guard([&] {
+    if (!a || !out) fail(NK_ERR_INVALID_ARG, "sum: NULL");
+    TensorP od;
+    nkg_var* v = unary_node(a, Shape{}, NK_F32, od);
+    auto op = std::make_shared<SumMean>();
+    op->ctx = a->ctx;
+    op->operand = a->data;
+    op->data = od;
+    op->mean = mean;
+    uint64_t id = push(v, op);
+    if (a->diff()) {
+      v->grad = std::make_shared<Gradient>(a->ctx, Shape{}, NK_F32);
+      auto bw = std::make_shared<SumMeanBackward>();
+      bw->ctx = a->ctx;
+      bw->gradient = v->grad;
+      bw->operand_grad = a->grad;
+      bw->mean = mean;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+int nkg_sum(nkg_var* a, nkg_var** out) { return summean_impl(a, false, out); }
+int nkg_mean(nkg_var* a, nkg_var** out) { return summean_impl(a, true, out); }
+
+static int loss_impl(nkg_var* input, nkg_var* target, int reduction, bool nll, nkg_var** out) {
+  return guard([&] {
+    if (!input || !target || !out) fail(NK_ERR_INVALID_ARG, "loss: NULL");
+    require_same_dtype(input, target, nll ? "nll_loss" : "mse_loss");
+    if (nll) {
+      if (input->data->shape.size() != 2 || target->data->shape.size() != 1 ||
+          target->data->shape[0] != input->data->shape[0])
+        fail(NK_ERR_INVALID_ARG, "nll_loss: input must be (N, C) and target (N)");
+    } else if (input->data->shape != target->data->shape) {
+      fail(NK_ERR_INVALID_ARG, "mse_loss: input and target shapes differ");
+    }
+    if (target->diff()) fail(NK_ERR_INVALID_ARG, "loss: the target must not be differentiable");
+    nkg_var* v = new_like(input);
+    merge(v, input, target);
+    v->data = std::make_shared<Tensor>(input->ctx, Shape{}, NK_F32);
+    auto op = std::make_shared<Loss>();
+    op->ctx = input->ctx;
+    op->input = input->data;
+    op->target = target->data;
+    op->data = v->data;
+    op->mean = reduction == NKG_MEAN;
+    op->nll = nll;
+    uint64_t id = push(v, op);
+    if (input->diff()) {
+      v->grad = std::make_shared<Gradient>(input->ctx, Shape{}, NK_F32);
+      auto bw = std::make_shared<LossBackward>();
+      bw->ctx = input->ctx;
+      bw->gradient = v->grad;
+      bw->input = input->data;
+      bw->target = target->data;
+      bw->input_grad = input->grad;
+      bw->mean = op->mean;
+      bw->nll = nll;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+int nkg_mse_loss(nkg_var* i, nkg_var* t, int r, nkg_var** o) { return loss_impl(i, t, r, false, o); }
+int nkg_nll_loss(nkg_var* i, nkg_var* t, int r, nkg_var** o) { return loss_impl(i, t, r, true, o); }
+
+int nkg_pad(nkg_var* a, int64_t ph, int64_t pw, float value, nkg_var** out) {
+  return guard([&] {
+    if (!a || !out) fail(NK_ERR_INVALID_ARG, "pad: NULL");
+    const Shape& s = a->data->shape;
+    if (s.size() != 4 || ph < 0 || pw < 0) fail(NK_ERR_INVALID_ARG, "pad: expects a (N, C, H, W) operand and padding >= 0");
+    TensorP od;
+    nkg_var* v = unary_node(a, Shape{s[0], s[1], s[2] + 2 * ph, s[3] + 2 * pw}, a->data->dtype, od);
+    auto op = std::make_shared<Pad>();
+    op->ctx = a->ctx;
+    op->operand = a->data;
+    op->data = od;
+    op->ph = ph;
+    op->pw = pw;
+    op->value = value;
+    uint64_t id = push(v, op);
+    if (a->diff()) {
+      v->grad = std::make_shared<Gradient>(a->ctx, od->shape, od->dtype);
+      auto bw = std::make_shared<PadBackward>();
+      bw->ctx = a->ctx;
+      bw->gradient = v->grad;
+      bw->operand_grad = a->grad;
+      bw->ph = ph;
+      bw->pw = pw;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+
+int nkg_convolution(nkg_var* kernel, nkg_var* input, int64_t sh, int64_t sw, int64_t dh, int64_t dw, int64_t groups,
+                    nkg_var** out) {
+  return guard([&] {
+    if (!kernel || !input || !out) fail(NK_ERR_INVALID_ARG, "convolution: NULL");
+    require_same_dtype(kernel, input, "convolution");
+    const Shape &ks = kernel->data->shape, &is = input->data->shape;
+    // check_conv_args / check_groups_args, utils.rs:427-496 (same messages)
+    if (is.size() != 4) fail(NK_ERR_UNSUPPORTED, "convolution: only 2d convolutions (N, C, H, W) run on the device");
+    if (ks.size() != is.size()) fail(NK_ERR_INVALID_ARG, "Invalid kernel shape for 2d conv");
+    if (sh < 1 || sw < 1 || dh < 1 || dw < 1 || groups < 1) fail(NK_ERR_INVALID_ARG, "Invalid stride/dilation/groups for 2d conv.");
+    if (is[2] < (ks[2] - 1) * dh + 1 || is[3] < (ks[3] - 1) * dw + 1)
+      fail(NK_ERR_INVALID_ARG, "The kernel size can't be greater than actual input size.");
+    if (is[1] % groups) fail(NK_ERR_INVALID_ARG, "In channels %lld is not divisible by groups %lld", (long long)is[1], (long long)groups);
+    if (ks[0] % groups) fail(NK_ERR_INVALID_ARG, "Out channels %lld is not divisible by groups %lld", (long long)ks[0], (long long)groups);
+    if (ks[1] * groups != is[1]) fail(NK_ERR_INVALID_ARG, "convolution: kernel in-channels %lld x groups %lld != input channels %lld", (long long)ks[1], (long long)groups, (long long)is[1]);
+    ConvArgs a{is[0], is[1], is[2], is[3], ks[0], ks[2], ks[3], sh, sw, dh, dw, groups};
+    Shape os{is[0], ks[0], (is[2] - dh * (ks[2] - 1) - 1) / sh + 1, (is[3] - dw * (ks[3] - 1) - 1) / sw + 1};
+    nkg_var* v = new_like(kernel);
+    merge(v, kernel, input);
+    v->data = std::make_shared<Tensor>(kernel->ctx, os, input->data->dtype);
+    auto op = std::make_shared<Convolution>();
+    op->ctx = kernel->ctx;
+    op->input = input->data;
+    op->kernel = kernel->data;
+    op->data = v->data;
+    op->a = a;
+    uint64_t id = push(v, op);
+    if (kernel->diff() || input->diff()) {
+      v->grad = std::make_shared<Gradient>(kernel->ctx, os, input->data->dtype);
+      auto bw = std::make_shared<ConvolutionBackward>();
+      bw->ctx = kernel->ctx;
+      bw->gradient = v->grad;
+      bw->input = input->data;
+      bw->kernel = kernel->data;
+      bw->input_grad = input->grad;
+      bw->kernel_grad = kernel->grad;
+      bw->a = a;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+
+int nkg_flatten(nkg_var* a, nkg_var** out) {
+  return guard([&] {
+    if (!a || !out) fail(NK_ERR_INVALID_ARG, "flatten: NULL");
+    const Shape& s = a->data->shape;
+    if (s.size() < 2) fail(NK_ERR_INVALID_ARG, "flatten: needs at least 2 dimensions");
+    int64_t rest = 1;
+    for (size_t i = 1; i < s.size(); ++i) rest *= s[i];
+    nkg_var* v = new nkg_var(*a);  // same tapes: a view records no node
+    auto t = std::make_shared<Tensor>(a->ctx, Shape{s[0], rest}, a->data->dtype);
+    t->base = a->data;
+    t->owned = false;
+    v->data = t;
+    if (a->diff()) {
+      // the gradient of a view is the same memory with the view's shape
+      auto g = std::make_shared<Gradient>(a->ctx, Shape{s[0], rest}, a->grad->dtype);
+      g->alias = a->grad;
+      v->grad = g;
+    }
+    v->fwd_buf.clear();
+    v->bwd_buf.clear();
+    *out = v;
+  });
+}
+
+int nkg_sgd_step(nkg_var* p, float* momentum_buf, float* master, float lr, float l2, float momentum, float dampening,
+                 int nesterov, float grad_scale) {
+  return guard([&] {
+    if (!p || !p->diff()) fail(NK_ERR_INVALID_ARG, "sgd: parameter is not differentiable");
+    Gradient* g = p->grad->root();
+    ck(p->ctx, nk_sgd_step(p->ctx, p->data->rptr(), p->data->dtype, p->grad->get(), g->dtype, momentum_buf, master,
+                           size_t(p->data->n()), lr, l2, momentum, dampening, nesterov, grad_scale, 1));
+    g->is_zero = false;
+  });
+}
+
+}  // extern "C"

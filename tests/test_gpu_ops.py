@@ -449,3 +449,35 @@ def test_conv2d_random_f32(nk, dev, O, stride, dil, groups):
     O.conv_backward_kernel(ww, g, x, stride, dil, groups)
     assert close_f32(gx.as_ndarray(), wx, 64) and close_f32(gw.as_ndarray(), ww, 400)
     assert np.allclose(gb.as_ndarray().ravel(), g.sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("shape,cout,k", [((2, 3, 20, 24), 64, (3, 3)), ((1, 3, 224, 224), 64, (3, 3)),
+                                          ((3, 8, 17, 40), 32, (3, 3)), ((2, 5, 9, 72), 100, (2, 4)),
+                                          ((2, 32, 12, 32), 64, (3, 3)), ((1, 1, 6, 8), 1, (1, 1))])
+def test_conv2d_tensor_core_forward(nk, dev, O, shape, cout, k):
+    """bf16 stride-1 convolution on the tcgen05 implicit-GEMM engine vs the oracle on the same bf16-rounded
+    operands (f32 accumulate); bias + ReLU fused in the epilogue; ragged widths (Wo not a multiple of 64)."""
+    from neuronika_b200 import ops
+    rng = np.random.default_rng(11)
+    x = O.bf16_round(rnd(rng, shape, 0, 1))
+    w = O.bf16_round(rnd(rng, (cout, shape[1]) + k, -0.3, 0.3))
+    b = O.bf16_round(rnd(rng, (cout,), -0.2, 0.2))
+    dx_, dw_, db_ = dev.from_ndarray(x, nk.BF16), dev.from_ndarray(w, nk.BF16), dev.from_ndarray(b, nk.BF16)
+    y = ops.conv2d(dx_, dw_)
+    assert dev.last_conv_kernel == "tcgen05_implicit_gemm_fwd"
+    want = O.conv_forward(x, w, (1, 1), (1, 1)).astype(np.float64)
+    scale = float(np.sqrt((want ** 2).mean())) + 1e-9
+    err = np.abs(y.as_ndarray() - want)
+    assert np.all(err <= 2e-3 * scale + 2.0 ** -8 * np.abs(want)), float(err.max())
+    yb = ops.conv2d(dx_, dw_, bias=db_, relu=True)
+    wb = np.maximum(want + b[None, :, None, None], 0)
+    assert np.all(np.abs(yb.as_ndarray() - wb) <= 2e-3 * scale + 2.0 ** -8 * np.abs(wb))
+    # the direct engine gives the same numbers up to bf16 rounding of the output
+    import os
+    os.environ["NK_CONV_DIRECT"] = "1"
+    try:
+        yd = ops.conv2d(dx_, dw_)
+        assert dev.last_conv_kernel == "direct_fwd"
+    finally:
+        del os.environ["NK_CONV_DIRECT"]
+    assert np.all(np.abs(yd.as_ndarray() - y.as_ndarray()) <= 2e-3 * scale + 2.0 ** -7 * np.abs(want))
