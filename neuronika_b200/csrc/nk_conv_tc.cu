@@ -23,10 +23,6 @@
 #include "nk_internal.cuh"
 #include "nk_ptx.cuh"
 
-int nk_conv2d_bwd_kernel_tc(nk_ctx*, void*, int, void*, const void*, const void*, int64_t, int64_t, int64_t, int64_t,
-                            int64_t, int64_t, int64_t, float) {
-  return NK_ERR_UNSUPPORTED;
-}
 int nk_conv2d_bwd_input_tc(nk_ctx*, void*, const void*, const void*, int64_t, int64_t, int64_t, int64_t, int64_t,
                            int64_t, int64_t, float) {
   return NK_ERR_UNSUPPORTED;
@@ -34,19 +30,21 @@ int nk_conv2d_bwd_input_tc(nk_ctx*, void*, const void*, const void*, int64_t, in
 
 namespace {
 
-constexpr int kThreads = 320;      // warp 0: TMA, warp 1: MMA + TMEM, warps 2..9: epilogue (2 per TMEM lane quarter)
-constexpr int kEpiThreads = 256;
+// warp roles of the forward kernel
+constexpr int kThreads = 448;      // warp 0: TMA, warp 1: MMA + TMEM, warps 2..5: shift, warps 6..13: epilogue
+constexpr int kShiftWarp0 = 2, kShiftThreads = 128;
+constexpr int kEpiWarp0 = 6, kEpiThreads = 256;
 constexpr int kChunk = 64;         // pixels per chunk (128 bytes of bf16)
 constexpr int kChunksPerTile = 4;  // UMMA N = 256
-constexpr int kStageBytes = kChunksPerTile * 16 * 128;  // 4 chunks x 16 K-rows x 128 B = 8 KB
-constexpr int kStages = 8;
-constexpr int kMaxKBlocks = 5;     // resident weight tiles of 16 KB (K <= 320)
+constexpr int kSlotBytes = kChunksPerTile * 16 * 128;   // one tap: 4 chunks x 16 K-rows x 128 B = 8 KB
+constexpr int kHaloBytes = kChunksPerTile * 256;        // 4 chunks x 16 rows x 16 B
+constexpr int kMaxKBlocks = 6;     // resident weight tiles of 16 KB (K <= 384)
 
 struct ConvP {
   int n, cin, h, w, cout, kh, kw, ho, wo;
   int cpr, chunks_per_img, tiles_per_img, num_tiles;
-  int cpg, ng, ksteps, kblocks;
-  int vec;  // store vector width in elements (1, 2, 4 or 8), from the alignment of Wo
+  int cpg, ng, ksteps, kblocks, R, stages;
+  int vec;  // store vector width in elements (1 or 2), from the alignment of Wo
   const __nv_bfloat16* wt;
   const __nv_bfloat16* bias;
   __nv_bfloat16* y;
@@ -58,35 +56,69 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// byte offset of 32-bit word `w` of row `r` in a [rows][128 B] SWIZZLE_128B tile (1024-byte aligned base)
+__device__ __forceinline__ uint32_t sw128_word(int r, int w) {
+  return uint32_t(r) * 128u + (uint32_t(((w >> 2) ^ (r & 7))) << 4) + uint32_t(w & 3) * 4u;
+}
+
+// TMA can only start a box on a 16-byte boundary (profiles/r01_tma_alignment_probe.md), so the horizontal taps
+// j >= 1 are produced here: out[px] = in[px + j] for the R live K-rows of each chunk, reading the tap-0 window
+// (swizzled, written by TMA) plus the 8-pixel halo box, writing the swizzled tap-j slot.
+__device__ __forceinline__ void shift_taps(uint8_t* stage_ptr, int kw, int R, int t) {
+  const uint8_t* halo = stage_ptr + kw * kSlotBytes;
+  const int lane = t & 31, wrp = t >> 5;
+  // one warp per (chunk, row): lane = 32-bit word of the 128-byte row; word 32.. come from the halo box
+  for (int c = 0; c < kChunksPerTile; ++c)
+  for (int r = wrp; r < R; r += kShiftThreads / 32) {
+    const uint8_t* rawrow = stage_ptr + c * 2048;
+    const uint32_t own = *reinterpret_cast<const uint32_t*>(rawrow + sw128_word(r, lane));
+    const uint32_t hl = *reinterpret_cast<const uint32_t*>(halo + c * 256 + r * 16 + (lane & 3) * 4);  // halo word lane&3
+    const uint32_t dst_off = c * 2048 + sw128_word(r, lane);
+    for (int j = 1; j < kw; ++j) {
+      const int ws = j >> 1;
+      // word(lane + ws) and word(lane + ws + 1) of the 36-word extended row
+      const int i0 = lane + ws, i1 = i0 + 1;
+      uint32_t lo = __shfl_sync(0xffffffffu, own, i0 & 31);
+      uint32_t hi = __shfl_sync(0xffffffffu, own, i1 & 31);
+      const uint32_t h0 = __shfl_sync(0xffffffffu, hl, i0 & 3), h1 = __shfl_sync(0xffffffffu, hl, i1 & 3);
+      if (i0 >= 32) lo = h0;
+      if (i1 >= 32) hi = h1;
+      const uint32_t out = (j & 1) ? __funnelshift_r(lo, hi, 16) : lo;
+      *reinterpret_cast<uint32_t*>(stage_ptr + j * kSlotBytes + dst_off) = out;
+    }
+  }
+}
+
+template <bool kBias, bool kRelu>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvP p) {
+conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_halo,
+                   const ConvP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
-  // layout: [weights kblocks x 16 KB][stages x 8 KB][staging 2 x 4 chunks x rows x 128 B][barriers]
-  const int rows = (p.cout + 31) & ~31;                     // staged output rows (multiple of 32)
-  const uint32_t w_off = 0;
-  const uint32_t st_off = w_off + p.kblocks * 16384;
-  const uint32_t sg_off = st_off + kStages * kStageBytes;
-  const uint32_t sg_buf_bytes = kChunksPerTile * rows * 128;
-  const uint32_t bar_off = sg_off + 2 * sg_buf_bytes;
+  // layout: [weights kblocks x 16 KB][stages x (kw tap slots + halo)][staging 4 chunks x rows x 128 B][barriers]
+  const int rows = (p.cout + 31) & ~31;
+  const uint32_t stage_bytes = p.kw * kSlotBytes + kHaloBytes;
+  const uint32_t st_off = p.kblocks * 16384;
+  const uint32_t sg_off = st_off + p.stages * stage_bytes;
+  const uint32_t bar_off = sg_off + kChunksPerTile * rows * 128;
   const uint32_t bar_base = base + bar_off;
+  const int S = p.stages;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (2 * kStages + 4));
+  auto ready_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (3 * S + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (3 * S + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * S + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (3 * S + 4));
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- one-time setup: zero the stage ring (K-rows the boxes never write must be 0), weights -> smem
+  // ---- one-time setup: zero weights + stage ring (K-rows no box ever writes must be 0), then weights -> smem
   {
-    uint4* z = reinterpret_cast<uint4*>(base_ptr + st_off);
-    for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
-    uint4* wz = reinterpret_cast<uint4*>(base_ptr + w_off);
-    for (int i = threadIdx.x; i < p.kblocks * 16384 / 16; i += kThreads) wz[i] = make_uint4(0, 0, 0, 0);
+    uint4* z = reinterpret_cast<uint4*>(base_ptr);
+    for (uint32_t i = threadIdx.x; i < sg_off / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   {
@@ -99,13 +131,15 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvP p) {
       const int kk = (j * p.ng + grp) * 16 + cl * p.kh + i;
       const int blk = kk >> 6, col = kk & 63;
       const uint32_t off = blk * 16384 + co * 128 + (((col >> 3) ^ (co & 7)) << 4) + (col & 7) * 2;
-      *reinterpret_cast<__nv_bfloat16*>(base_ptr + w_off + off) = p.wt[idx];
+      *reinterpret_cast<__nv_bfloat16*>(base_ptr + off) = p.wt[idx];
     }
   }
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
-    for (int s = 0; s < kStages; ++s) {
+    ptx::prefetch_tmap(&tmap_halo);
+    for (int s = 0; s < S; ++s) {
       ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(ready_bar(s), kShiftThreads / 32);
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -124,21 +158,19 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvP p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const uint32_t box_bytes = 64u * 2u * p.kh * p.cpg;
-
   if (warp_idx == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== TMA producer: tap-0 windows + 8-pixel halos
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t tx = kChunksPerTile * (64u + 8u) * 2u * p.R;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int n = tile / p.tiles_per_img;
         const int g0 = (tile - n * p.tiles_per_img) * kChunksPerTile;
-        for (int ks = 0; ks < p.ksteps; ++ks) {
-          const int j = ks / p.ng, grp = ks - j * p.ng;
+        for (int grp = 0; grp < p.ng; ++grp) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          ptx::mbar_expect_tx(full_bar(stage), kChunksPerTile * box_bytes);
-          const uint32_t sb = base + st_off + stage * kStageBytes;
+          ptx::mbar_expect_tx(full_bar(stage), tx);
+          const uint32_t sb = base + st_off + stage * stage_bytes;
 #pragma unroll
           for (int c = 0; c < kChunksPerTile; ++c) {
             const int g = g0 + c;
@@ -147,9 +179,11 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvP p) {
               prow = g / p.cpr;
               qcol = (g - prow * p.cpr) * kChunk;
             }
-            ptx::tma_load_4d(sb + c * 2048, &tmap_x, full_bar(stage), qcol + j, prow, grp * p.cpg, n);
+            ptx::tma_load_4d(sb + c * 2048, &tmap_x, full_bar(stage), qcol, prow, grp * p.cpg, n);
+            ptx::tma_load_4d(sb + p.kw * kSlotBytes + c * 256, &tmap_halo, full_bar(stage), qcol + kChunk, prow,
+                             grp * p.cpg, n);
           }
-          if (++stage == kStages) {
+          if (++stage == S) {
             stage = 0;
             phase ^= 1u;
           }
@@ -168,15 +202,18 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvP p) {
         ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(as * 256);
-        for (int ks = 0; ks < p.ksteps; ++ks) {
-          ptx::mbar_wait(full_bar(stage), phase);
+        for (int grp = 0; grp < p.ng; ++grp) {
+          ptx::mbar_wait(ready_bar(stage), phase);
           ptx::tc_fence_after();
-          const uint64_t adesc =
-              ptx::make_smem_desc_sw128(base + w_off + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-          const uint64_t bdesc = ptx::make_smem_desc_sw128(base + st_off + stage * kStageBytes, 2048, 1024);
-          ptx::mma_f16_ss(tmem_d, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
+          const uint32_t sb = base + st_off + stage * stage_bytes;
+          for (int j = 0; j < p.kw; ++j) {
+            const int ks = j * p.ng + grp;
+            const uint64_t adesc = ptx::make_smem_desc_sw128(base + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + j * kSlotBytes, 2048, 1024);
+            ptx::mma_f16_ss(tmem_d, adesc, bdesc, idesc, (grp | j) != 0 ? 1u : 0u);
+          }
           ptx::mma_commit(empty_bar(stage));
-          if (++stage == kStages) {
+          if (++stage == S) {
             stage = 0;
             phase ^= 1u;
           }
@@ -186,23 +223,39 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvP p) {
         if (as == 0) aphase ^= 1u;
       }
     }
+  } else if (warp_idx < kEpiWarp0) {
+    // ===================================================== shift warps: taps j >= 1 from the tap-0 window
+    const int t = threadIdx.x - kShiftWarp0 * 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int grp = 0; grp < p.ng; ++grp) {
+        ptx::mbar_wait(full_bar(stage), phase);
+        shift_taps(base_ptr + st_off + stage * stage_bytes, p.kw, p.R, t);
+        ptx::fence_proxy_async();  // these generic-proxy writes are read by the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ready_bar(stage));
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
   } else {
     // ===================================================== epilogue: TMEM -> regs -> swizzled smem -> NCHW rows
     const int q = warp_idx & 3;          // TMEM lane quarter this warp may read
-    const int ew = warp_idx - 2;         // 0..7 rank among epilogue warps (row striping of the copy-out)
+    const int ew = warp_idx - kEpiWarp0; // 0..7 rank among epilogue warps (row striping of the copy-out)
     const int c_begin = (ew >> 2) * 2;   // the two warps of a quarter split the tile's chunks: {0,1} and {2,3}
     const int co = q * 32 + lane;
     const bool row_active = co < rows;
-    const float bias_v = (p.bias && co < p.cout) ? __bfloat162float(p.bias[co]) : 0.f;
+    const float bias_v = (kBias && co < p.cout) ? __bfloat162float(p.bias[co]) : 0.f;
     int as = 0;
     uint32_t aphase = 0;
-    int buf = 0;
     const int64_t plane = int64_t(p.ho) * p.wo;
+    uint8_t* sg = base_ptr + sg_off;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n = tile / p.tiles_per_img;
       const int g0 = (tile - n * p.tiles_per_img) * kChunksPerTile;
-      uint8_t* sg = base_ptr + sg_off + buf * sg_buf_bytes;
-      // the copy-out of the tile that used this buffer two tiles ago finished before the barrier at its end
       ptx::mbar_wait(tmem_full_bar(as), aphase);
       ptx::tc_fence_after();
       if (q * 32 < rows) {
@@ -221,9 +274,13 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvP p) {
                 uint32_t w4[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  float a = __uint_as_float(r[v * 8 + e * 2]) + bias_v;
-                  float b = __uint_as_float(r[v * 8 + e * 2 + 1]) + bias_v;
-                  if (p.relu) {
+                  float a = __uint_as_float(r[v * 8 + e * 2]);
+                  float b = __uint_as_float(r[v * 8 + e * 2 + 1]);
+                  if (kBias) {
+                    a += bias_v;
+                    b += bias_v;
+                  }
+                  if (kRelu) {
                     a = a > 0.f ? a : 0.f;
                     b = b > 0.f ? b : 0.f;
                   }
@@ -238,38 +295,59 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const ConvP p) {
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // staging complete (epilogue warps only)
-      // ---- coalesced copy-out: each warp takes rows ew, ew+4, ...; a row is 64 pixels = 128 B
-      for (int c = 0; c < kChunksPerTile; ++c) {
-        const int g = g0 + c;
-        if (g >= p.chunks_per_img) break;
-        const int prow = g / p.cpr, q0 = (g - prow * p.cpr) * kChunk;
+      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));  // accumulator drained: the next tile's MMAs may start
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // staging complete (epilogue warps only)
+      // ---- coalesced copy-out: each warp takes rows ew, ew+8, ...; a row is 64 pixels = 128 B.
+      // rr & 7 == ew & 7 for every row of this warp, so the swizzled lane offset is loop invariant.
+      int prow = g0 / p.cpr, qc = g0 - prow * p.cpr;
+      for (int c = 0; c < kChunksPerTile; ++c, ++qc) {
+        if (g0 + c >= p.chunks_per_img) break;
+        if (qc == p.cpr) {
+          qc = 0;
+          ++prow;
+        }
+        const int q0 = qc * kChunk;
         const int valid = min(kChunk, p.wo - q0);
-        for (int rr = ew; rr < p.cout; rr += kEpiThreads / 32) {
-          const uint8_t* rowp = sg + (c * rows + rr) * 128;
-          __nv_bfloat16* dst = p.y + (int64_t(n) * p.cout + rr) * plane + int64_t(prow) * p.wo + q0;
-          if (p.vec >= 2) {
-            // lane handles pixels 2*lane, 2*lane+1 (4 bytes); dst is 4-byte aligned because Wo is even
-            const int px = lane * 2;
-            const int c16 = (px >> 3) ^ (rr & 7);
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(rowp + c16 * 16 + (px & 7) * 2);
-            if (px + 1 < valid)
-              *reinterpret_cast<uint32_t*>(dst + px) = v;
-            else if (px < valid)
-              dst[px] = *reinterpret_cast<const __nv_bfloat16*>(&v);
-          } else {
+        __nv_bfloat16* dst = p.y + (int64_t(n) * p.cout + ew) * plane + int64_t(prow) * p.wo + q0;
+        const uint8_t* rowp = sg + (c * rows + ew) * 128;
+        const int64_t dstep = 8 * plane;
+        if (p.vec >= 2) {
+          const int px = lane * 2;
+          const uint8_t* src = rowp + ((((px >> 3) ^ (ew & 7))) << 4) + (px & 7) * 2;
+          __nv_bfloat16* d2 = dst + px;
+          if (px + 1 < valid) {
+            const int nrows = (p.cout - ew + 7) >> 3;
+            int k = 0;
+            for (; k + 4 <= nrows; k += 4) {  // 4 independent load/store pairs in flight
+              const uint32_t v0 = *reinterpret_cast<const uint32_t*>(src + (k + 0) * 1024);
+              const uint32_t v1 = *reinterpret_cast<const uint32_t*>(src + (k + 1) * 1024);
+              const uint32_t v2 = *reinterpret_cast<const uint32_t*>(src + (k + 2) * 1024);
+              const uint32_t v3 = *reinterpret_cast<const uint32_t*>(src + (k + 3) * 1024);
+              *reinterpret_cast<uint32_t*>(d2 + (k + 0) * dstep) = v0;
+              *reinterpret_cast<uint32_t*>(d2 + (k + 1) * dstep) = v1;
+              *reinterpret_cast<uint32_t*>(d2 + (k + 2) * dstep) = v2;
+              *reinterpret_cast<uint32_t*>(d2 + (k + 3) * dstep) = v3;
+            }
+            for (; k < nrows; ++k)
+              *reinterpret_cast<uint32_t*>(d2 + k * dstep) = *reinterpret_cast<const uint32_t*>(src + k * 1024);
+          } else if (px < valid) {
+            for (int rr = ew; rr < p.cout; rr += 8, src += 1024, d2 += dstep)
+              *d2 = *reinterpret_cast<const __nv_bfloat16*>(src);
+          }
+        } else {
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int px = lane + hh * 32;
-              const int c16 = (px >> 3) ^ (rr & 7);
-              if (px < valid) dst[px] = *reinterpret_cast<const __nv_bfloat16*>(rowp + c16 * 16 + (px & 7) * 2);
+          for (int hh = 0; hh < 2; ++hh) {
+            const int px = lane + hh * 32;
+            if (px < valid) {
+              const uint8_t* src = rowp + ((((px >> 3) ^ (ew & 7))) << 4) + (px & 7) * 2;
+              __nv_bfloat16* d1 = dst + px;
+              for (int rr = ew; rr < p.cout; rr += 8, src += 1024, d1 += dstep)
+                *d1 = *reinterpret_cast<const __nv_bfloat16*>(src);
             }
           }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // buffer may be overwritten two tiles from now
-      buf ^= 1;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // staging buffer free again
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
@@ -287,6 +365,20 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// x as a 4-D (W, H, C, N) bf16 tensor; box {box_w, kh, cpg, 1}
+int make_x_tmap(nk_ctx* ctx, CUtensorMap* tm, const void* x, int64_t n, int64_t cin, int64_t h, int64_t wd, int box_w,
+                int kh, int cpg, bool swizzle) {
+  cuuint64_t dims[4] = {(cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)cin, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)wd * 2, (cuuint64_t)wd * h * 2, (cuuint64_t)wd * h * cin * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_w, (cuuint32_t)kh, (cuuint32_t)cpg, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NK_OK : NK_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 
 int nk_conv2d_fwd_tc(nk_ctx* ctx, void* y, const void* x, const void* w, const void* bias, int relu, int64_t n,
@@ -295,13 +387,14 @@ int nk_conv2d_fwd_tc(nk_ctx* ctx, void* y, const void* x, const void* w, const v
   if (!ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
   // TMA addressing: 16-byte aligned base, every global stride a multiple of 16 bytes  => W % 8 == 0
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (wd % 8) != 0) return NK_ERR_UNSUPPORTED;
-  if (kh > 16 || kh < 1 || kw < 1 || cout > 128 || cout < 1) return NK_ERR_UNSUPPORTED;
+  if (kh > 16 || kh < 1 || kw < 1 || kw > 8 || cout > 128 || cout < 1) return NK_ERR_UNSUPPORTED;
   if (n > 65535 || h > (1 << 20) || wd > (1 << 20)) return NK_ERR_UNSUPPORTED;
   ConvP p;
   p.n = (int)n, p.cin = (int)cin, p.h = (int)h, p.w = (int)wd, p.cout = (int)cout, p.kh = (int)kh, p.kw = (int)kw;
   p.ho = int(h - kh + 1), p.wo = int(wd - kw + 1);
   p.cpg = 16 / p.kh;
   if (p.cpg > p.cin) p.cpg = p.cin;
+  p.R = p.cpg * p.kh;
   p.ng = (p.cin + p.cpg - 1) / p.cpg;
   p.ksteps = p.kw * p.ng;
   p.kblocks = (p.ksteps * 16 + 63) / 64;
@@ -318,29 +411,353 @@ int nk_conv2d_fwd_tc(nk_ctx* ctx, void* y, const void* x, const void* w, const v
   p.y = static_cast<__nv_bfloat16*>(y);
   p.relu = relu;
   const int rows = (p.cout + 31) & ~31;
-  const size_t smem = 1024 + size_t(p.kblocks) * 16384 + size_t(kStages) * kStageBytes +
-                      2 * size_t(kChunksPerTile) * rows * 128 + 512;
-  if (smem > 232448) return NK_ERR_UNSUPPORTED;
+  const size_t stage_bytes = size_t(p.kw) * kSlotBytes + kHaloBytes;
+  const size_t fixed = 1024 + size_t(p.kblocks) * 16384 + size_t(kChunksPerTile) * rows * 128 + 512;
+  if (fixed + 2 * stage_bytes > 232448) return NK_ERR_UNSUPPORTED;
+  p.stages = int((232448 - fixed) / stage_bytes);
+  if (p.stages > 6) p.stages = 6;
+  const size_t smem = fixed + size_t(p.stages) * stage_bytes;
 
-  CUtensorMap tm;
-  cuuint64_t dims[4] = {(cuuint64_t)wd, (cuuint64_t)h, (cuuint64_t)cin, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)wd * 2, (cuuint64_t)wd * h * 2, (cuuint64_t)wd * h * cin * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)p.kh, (cuuint32_t)p.cpg, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-      &tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return NK_ERR_UNSUPPORTED;
+  CUtensorMap tm, tmh;
+  if (make_x_tmap(ctx, &tm, x, n, cin, h, wd, 64, p.kh, p.cpg, true) != NK_OK) return NK_ERR_UNSUPPORTED;
+  if (make_x_tmap(ctx, &tmh, x, n, cin, h, wd, 8, p.kh, p.cpg, false) != NK_OK) return NK_ERR_UNSUPPORTED;
 
   static bool attr_done = false;
   if (!attr_done) {
-    NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_done = true;
   }
   const int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-  conv_fwd_tc_kernel<<<grid, kThreads, smem, ctx->stream>>>(tm, p);
+  if (bias && relu)
+    conv_fwd_tc_kernel<true, true><<<grid, kThreads, smem, ctx->stream>>>(tm, tmh, p);
+  else if (bias)
+    conv_fwd_tc_kernel<true, false><<<grid, kThreads, smem, ctx->stream>>>(tm, tmh, p);
+  else if (relu)
+    conv_fwd_tc_kernel<false, true><<<grid, kThreads, smem, ctx->stream>>>(tm, tmh, p);
+  else
+    conv_fwd_tc_kernel<false, false><<<grid, kThreads, smem, ctx->stream>>>(tm, tmh, p);
   NK_LAUNCHED(ctx, "conv_fwd_tc");
   ctx->last_conv_kernel = "tcgen05_implicit_gemm_fwd";
+  return NK_OK;
+}
+
+// =====================================================================================================
+// dW (+ dbias): dW[co][k] += sum_px G[co][px] * Xwin[k][px]      (convolution/mod.rs:191-226, beta = 1)
+//
+// The reference streams the 1.36 GB column matrix once per output channel (64 GEMVs, ~87 GB of reads at
+// config 3).  Here G and x are each read once: per 64-pixel chunk
+//   A = G chunk   [Cout rows][64 px]  K-major SWIZZLE_128B, brought in by cp.async (G rows have a 2*Wo-byte
+//                 pitch, not a multiple of 16 bytes when Wo = 222, so TMA cannot address them)
+//   B = X windows [(j,grp,c,i) rows][64 px] K-major SWIZZLE_128B -- the same TMA boxes as the forward pass
+//   D[co][k] accumulates in TMEM across ALL chunks a CTA owns; one atomicAdd pass per CTA at the end.
+// dbias rides along: row 15 of the first B slot is all ones, so D[co][15] = sum_px G[co][px].
+// =====================================================================================================
+namespace {
+
+constexpr int kWThreads = 192;  // warp 0: TMA (x windows), warp 1: MMA + TMEM, warps 2..5: cp.async (G) then epilogue
+constexpr int kWProducers = 128;
+
+struct ConvWP {
+  int n, cin, h, w, cout, kh, kw, ho, wo;
+  int cpr, chunks_per_img;
+  long long total_chunks, chunks_per_cta;
+  int cpg, ng, ksteps, ncols, stages, fuse_dbias, R;
+  uint32_t tmem_cols;
+  const __nv_bfloat16* g;
+  float* scratch;
+};
+
+__global__ void __launch_bounds__(kWThreads, 1)
+conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_halo,
+                  const ConvWP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_u32);
+  const uint32_t x_bytes = p.ksteps * 2048;
+  const uint32_t halo_off = 16384 + x_bytes;
+  const uint32_t stage_bytes = halo_off + 1024;  // [G tile 128 x 128 B][X slots ksteps x 16 x 128 B][halo ng x 256 B]
+  const uint32_t bar_off = p.stages * stage_bytes;
+  const uint32_t bar_base = base + bar_off;
+  const int S = p.stages;
+  auto fullx_bar = [&](int s) { return bar_base + 8u * s; };
+  auto ready_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  const uint32_t done_bar = bar_base + 8u * (3 * S);
+  const uint32_t tmem_slot = bar_base + 8u * (3 * S + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (3 * S + 1));
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  {
+    uint4* z = reinterpret_cast<uint4*>(base_ptr);
+    for (uint32_t i = threadIdx.x; i < S * stage_bytes / 16; i += kWThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  if (p.fuse_dbias) {  // ones row: slot 0, row 15 (no box and no shift ever writes rows >= R, R <= 15 here)
+    for (int i = threadIdx.x; i < S * 32; i += kWThreads) {
+      const int s = i / 32, wq = i % 32;
+      *reinterpret_cast<uint32_t*>(base_ptr + s * stage_bytes + 16384 + 15 * 128 + wq * 4) = 0x3F803F80u;
+    }
+  }
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    ptx::prefetch_tmap(&tmap_halo);
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(fullx_bar(s), 1);
+      ptx::mbar_init(ready_bar(s), kWProducers + kWProducers / 32);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const long long ch_begin = (long long)blockIdx.x * p.chunks_per_cta;
+  long long ch_end = ch_begin + p.chunks_per_cta;
+  if (ch_end > p.total_chunks) ch_end = p.total_chunks;
+
+  if (warp_idx == 0) {
+    if (lane == 0) {  // TMA: tap-0 windows of every channel group + their 8-pixel halos
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = uint32_t(p.ng) * (64u + 8u) * 2u * p.R;
+      for (long long ch = ch_begin; ch < ch_end; ++ch) {
+        const int n = int(ch / p.chunks_per_img);
+        const int g = int(ch - (long long)n * p.chunks_per_img);
+        const int prow = g / p.cpr, q0 = (g - prow * p.cpr) * kChunk;
+        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        ptx::mbar_expect_tx(fullx_bar(stage), tx);
+        const uint32_t sx = base + stage * stage_bytes + 16384;
+        for (int grp = 0; grp < p.ng; ++grp) {
+          ptx::tma_load_4d(sx + grp * 2048, &tmap_x, fullx_bar(stage), q0, prow, grp * p.cpg, n);
+          ptx::tma_load_4d(base + stage * stage_bytes + halo_off + grp * 256, &tmap_halo, fullx_bar(stage), q0 + kChunk,
+                           prow, grp * p.cpg, n);
+        }
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, p.ncols, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool first = true;
+      for (long long ch = ch_begin; ch < ch_end; ++ch) {
+        ptx::mbar_wait(ready_bar(stage), phase);
+        ptx::fence_proxy_async();  // cp.async / st.shared (generic proxy) writes -> async proxy (UMMA)
+        ptx::tc_fence_after();
+        const uint32_t sa = base + stage * stage_bytes;
+        const uint64_t adesc = ptx::make_smem_desc_sw128(sa, 16, 1024);
+        const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + 16384, 16, 1024);
+#pragma unroll
+        for (int kq = 0; kq < 4; ++kq) {
+          ptx::mma_f16_ss(tmem_base, adesc + uint64_t(kq * 2), bdesc + uint64_t(kq * 2), idesc,
+                          (first && kq == 0) ? 0u : 1u);
+        }
+        first = false;
+        ptx::mma_commit(empty_bar(stage));
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      ptx::mma_commit(done_bar);
+    }
+  } else {
+    // ---- producers: cp.async G rows into the swizzled K-major A tile, then build the taps j >= 1 of the B tile
+    const int t = threadIdx.x - 64;  // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    const long long plane = (long long)p.ho * p.wo;
+    for (long long ch = ch_begin; ch < ch_end; ++ch) {
+      const int n = int(ch / p.chunks_per_img);
+      const int g = int(ch - (long long)n * p.chunks_per_img);
+      const int prow = g / p.cpr, q0 = (g - prow * p.cpr) * kChunk;
+      const int valid = min(kChunk, p.wo - q0);
+      ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t sa = base + stage * stage_bytes;
+      uint8_t* sp = base_ptr + stage * stage_bytes;
+      const __nv_bfloat16* gsrc = p.g + (long long)n * p.cout * plane + (long long)prow * p.wo + q0;
+      {
+        // thread t owns 4-byte piece (t & 31) of rows (t >> 5), (t >> 5) + 4, ...: everything but the row
+        // base is loop invariant, and (co & 7) only alternates between two values
+        const int piece = t & 31, co0 = t >> 5;
+        int nbytes = (valid - piece * 2) * 2;
+        nbytes = nbytes < 0 ? 0 : (nbytes > 4 ? 4 : nbytes);
+        const __nv_bfloat16* src = gsrc + (long long)co0 * plane + (nbytes ? piece * 2 : 0);
+        const long long sstep = 4 * plane;
+        const uint32_t sw0 = (((piece >> 2) ^ (co0 & 7)) << 4) + (piece & 3) * 4;
+        const uint32_t sw1 = (((piece >> 2) ^ ((co0 + 4) & 7)) << 4) + (piece & 3) * 4;
+        uint32_t drow = sa + co0 * 128;
+        for (int co = co0, it = 0; co < p.cout; co += 4, ++it, src += sstep, drow += 512) {
+          const uint32_t dst = drow + ((it & 1) ? sw1 : sw0);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ready_bar(stage)) : "memory");
+      // taps: slot(j*ng + grp)[r][px] = slot(grp)[r][px + j]   (tap-0 window + 8-pixel halo, see shift_taps)
+      ptx::mbar_wait(fullx_bar(stage), phase);
+      {
+        const uint8_t* halo = sp + halo_off;
+        const int wrp = t >> 5;
+        for (int grp = 0; grp < p.ng; ++grp)
+          for (int r = wrp; r < p.R; r += kWProducers / 32) {
+            const uint8_t* raw = sp + 16384 + grp * 2048;
+            const uint32_t own = *reinterpret_cast<const uint32_t*>(raw + sw128_word(r, lane));
+            const uint32_t hl = *reinterpret_cast<const uint32_t*>(halo + grp * 256 + r * 16 + (lane & 3) * 4);
+            const uint32_t doff = sw128_word(r, lane);
+            for (int j = 1; j < p.kw; ++j) {
+              const int i0 = lane + (j >> 1), i1 = i0 + 1;
+              uint32_t lo = __shfl_sync(0xffffffffu, own, i0 & 31);
+              uint32_t hi = __shfl_sync(0xffffffffu, own, i1 & 31);
+              const uint32_t h0 = __shfl_sync(0xffffffffu, hl, i0 & 3), h1 = __shfl_sync(0xffffffffu, hl, i1 & 3);
+              if (i0 >= 32) lo = h0;
+              if (i1 >= 32) hi = h1;
+              const uint32_t out = (j & 1) ? __funnelshift_r(lo, hi, 16) : lo;
+              *reinterpret_cast<uint32_t*>(sp + 16384 + (j * p.ng + grp) * 2048 + doff) = out;
+            }
+          }
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ready_bar(stage));
+      if (++stage == S) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    // ---- epilogue: one pass of atomics per CTA
+    ptx::mbar_wait(done_bar, 0);
+    ptx::tc_fence_after();
+    if (ch_end > ch_begin) {
+      const int q = warp_idx & 3;
+      const int co = q * 32 + lane;
+      if (q * 32 < p.cout) {
+        for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), r);
+          ptx::tmem_ld_wait();
+          if (co < p.cout) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) atomicAdd(&p.scratch[co * p.ncols + c0 + jj], __uint_as_float(r[jj]));
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+template <typename T>
+__global__ void conv_dw_finalize(T* __restrict__ dw, T* __restrict__ dbias, const float* __restrict__ scratch, int cout,
+                                 int cin, int kh, int kw, int cpg, int ng, int ncols, float beta, int fuse_dbias) {
+  const int per_co = cin * kh * kw;
+  const int total = cout * per_co;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total + cout; idx += gridDim.x * blockDim.x) {
+    if (idx < total) {
+      const int co = idx / per_co, r = idx - co * per_co;
+      const int c = r / (kh * kw), i = (r / kw) % kh, j = r % kw;
+      const int grp = c / cpg, cl = c - grp * cpg;
+      float v = scratch[co * ncols + (j * ng + grp) * 16 + cl * kh + i];
+      if (beta != 0.f) v += beta * nk_to_f32<T>(dw[idx]);
+      dw[idx] = nk_from_f32<T>(v);
+    } else if (fuse_dbias && dbias) {
+      const int co = idx - total;
+      float v = scratch[co * ncols + 15];
+      if (beta != 0.f) v += beta * nk_to_f32<T>(dbias[co]);
+      dbias[co] = nk_from_f32<T>(v);
+    }
+  }
+}
+
+}  // namespace
+
+int nk_conv2d_bwd_kernel_tc(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, const void* g, const void* x,
+                            int64_t n, int64_t cin, int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw,
+                            float beta) {
+  if (getenv("NK_CONV_DIRECT")) return NK_ERR_UNSUPPORTED;
+  if (!ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (wd % 8) != 0) return NK_ERR_UNSUPPORTED;
+  if (kh > 16 || kh < 1 || kw < 1 || kw > 8 || cout > 128 || cout < 1 || n > 65535) return NK_ERR_UNSUPPORTED;
+  ConvWP p;
+  p.n = (int)n, p.cin = (int)cin, p.h = (int)h, p.w = (int)wd, p.cout = (int)cout, p.kh = (int)kh, p.kw = (int)kw;
+  p.ho = int(h - kh + 1), p.wo = int(wd - kw + 1);
+  // cp.async moves 4-byte pieces of G rows: rows must start 4-byte aligned
+  if ((p.wo & 1) || (reinterpret_cast<uintptr_t>(g) & 3)) return NK_ERR_UNSUPPORTED;
+  p.cpg = 16 / p.kh;
+  if (p.cpg > p.cin) p.cpg = p.cin;
+  p.R = p.cpg * p.kh;
+  p.ng = (p.cin + p.cpg - 1) / p.cpg;
+  p.ksteps = p.kw * p.ng;
+  p.ncols = p.ksteps * 16;
+  if (p.ncols > 256 || p.ng > 4) return NK_ERR_UNSUPPORTED;
+  p.fuse_dbias = (dbias != nullptr && p.kh * p.cpg < 16) ? 1 : 0;
+  p.tmem_cols = p.ncols <= 32 ? 32 : p.ncols <= 64 ? 64 : p.ncols <= 128 ? 128 : 256;
+  p.cpr = (p.wo + kChunk - 1) / kChunk;
+  p.chunks_per_img = p.ho * p.cpr;
+  p.total_chunks = (long long)p.n * p.chunks_per_img;
+  const uint32_t stage_bytes = 16384 + p.ksteps * 2048 + 1024;
+  p.stages = int((232448 - 2048) / stage_bytes);
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages < 2) return NK_ERR_UNSUPPORTED;
+  int grid = ctx->sm_count;
+  if (p.total_chunks < grid) grid = (int)p.total_chunks;
+  p.chunks_per_cta = (p.total_chunks + grid - 1) / grid;
+  grid = int((p.total_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta);
+  p.g = static_cast<const __nv_bfloat16*>(g);
+  float* scratch;
+  int rc = nk_workspace(ctx, size_t(128) * p.ncols * sizeof(float), (void**)&scratch);
+  if (rc) return rc;
+  p.scratch = scratch;
+
+  CUtensorMap tm, tmh;
+  if (make_x_tmap(ctx, &tm, x, n, cin, h, wd, 64, p.kh, p.cpg, true) != NK_OK) return NK_ERR_UNSUPPORTED;
+  if (make_x_tmap(ctx, &tmh, x, n, cin, h, wd, 8, p.kh, p.cpg, false) != NK_OK) return NK_ERR_UNSUPPORTED;
+
+  if (dbias && !p.fuse_dbias) {
+    int64_t dshape[3] = {cout, 1, 1};
+    int64_t gshape[4] = {n, cout, p.ho, p.wo};
+    rc = nk_unbroadcast_acc(ctx, dbias, dw_dtype, 3, dshape, g, NK_BF16, 4, gshape, beta);
+    if (rc) return rc;
+    rc = nk_workspace(ctx, size_t(128) * p.ncols * sizeof(float), (void**)&scratch);
+    if (rc) return rc;
+    p.scratch = scratch;
+  }
+  NK_CUDA(ctx, cudaMemsetAsync(scratch, 0, size_t(128) * p.ncols * sizeof(float), ctx->stream));
+  static bool attr_done = false;
+  if (!attr_done) {
+    NK_CUDA(ctx, cudaFuncSetAttribute(conv_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_done = true;
+  }
+  const size_t smem = 1024 + size_t(p.stages) * stage_bytes + 512;
+  conv_dw_tc_kernel<<<grid, kWThreads, smem, ctx->stream>>>(tm, tmh, p);
+  NK_LAUNCHED(ctx, "conv_dw_tc");
+  const int total = int(cout * cin * kh * kw + cout);
+  const int blocks = (total + 255) / 256;
+  if (dw_dtype == NK_BF16)
+    conv_dw_finalize<__nv_bfloat16><<<blocks, 256, 0, ctx->stream>>>((__nv_bfloat16*)dwt, (__nv_bfloat16*)dbias, scratch, p.cout, p.cin, p.kh, p.kw, p.cpg, p.ng, p.ncols, beta, p.fuse_dbias);
+  else
+    conv_dw_finalize<float><<<blocks, 256, 0, ctx->stream>>>((float*)dwt, (float*)dbias, scratch, p.cout, p.cin, p.kh, p.kw, p.cpg, p.ng, p.ncols, beta, p.fuse_dbias);
+  NK_LAUNCHED(ctx, "conv_dw_finalize");
+  ctx->last_conv_kernel = "tcgen05_implicit_gemm_dw";
   return NK_OK;
 }

@@ -53,14 +53,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Wait with a watchdog: a protocol bug traps (and surfaces as a CUDA error) instead of
-// hanging the GPU.  ~2^32 cycles is seconds, far beyond any legitimate wait in these kernels.
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint
+// expires) instead of burning issue slots that the working warps of the same SM sub-partition need
+// (profiles/r01_conv_fwd_ncu.md: 25 % of all issued instructions were barrier polling before this).
+__device__ __forceinline__ bool mbar_try_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+// Wait with a watchdog: a protocol bug traps (and surfaces as a CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && (clock64() - t0) > (1ll << 32)) {
+  long long t0 = 0;
+  while (!mbar_try_wait_sleep(bar, parity)) {
+    if ((++spins & 63u) != 0) continue;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    if (now - t0 > (1ll << 32)) {  // ~2 s: far beyond any legitimate wait in these kernels
       printf("nk_b200: mbarrier watchdog: block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar,
              parity);
       __trap();

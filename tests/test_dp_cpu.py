@@ -1,0 +1,100 @@
+"""World-size-2 data-parallel host logic on CPU (gloo): batch sharding + flat gradient bucket + all-reduce(sum)
++ SGD with grad_scale = 1/world reproduces the single-process full-batch step of the oracle.
+No GPU, no device code: this covers the plumbing bench.py uses for N > 1."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+F32 = np.float32
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    import oracle as O
+    from neuronika_b200.parallel import BucketLayout, shard_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(0)                      # identical weights and data on every rank
+    sizes = [12, 16, 5]
+    params = []
+    for i, o in zip(sizes[:-1], sizes[1:]):
+        k = 1 / np.sqrt(i)
+        params.append((O.uniform_init(rng, (o, i), k), O.uniform_init(rng, (o,), k)))
+    x = rng.uniform(-1, 1, (8, sizes[0])).astype(F32)
+    t = np.eye(sizes[-1], dtype=F32)[rng.integers(0, sizes[-1], 8)]
+    lo, hi = shard_rows(8, rank, world)
+    shapes = [a.shape for p in params for a in p]
+    layout = BucketLayout(shapes)
+    flat = np.zeros(layout.total, F32)
+    views = layout.views(flat)
+    # local backward on the shard (lr = 0 keeps the weights; grads land in the bucket views)
+    local = [(w.copy(), b.copy()) for w, b in params]
+    _, grads = O.mlp_step(x[lo:hi], t[lo:hi], local, lr=0.0)
+    for li, (dw, db) in enumerate(grads):
+        views[2 * li][...] = dw
+        views[2 * li + 1][...] = db
+    tt = torch.from_numpy(flat)
+    dist.all_reduce(tt)                                  # sum over ranks, in place on the bucket
+    for li, (w, b) in enumerate(params):
+        O.sgd_step(w, views[2 * li] / world, 0.1)        # grad_scale = 1/world
+        O.sgd_step(b, views[2 * li + 1] / world, 0.1)
+    if rank == 0:
+        q.put([p.copy() for wb in params for p in wb])
+    dist.destroy_process_group()
+
+
+def test_bucket_layout_and_sharding():
+    from neuronika_b200.parallel import BucketLayout, shard_rows
+    lay = BucketLayout([(4, 3), (4,), (2, 4), (2,), ()])
+    assert lay.offsets == [0, 12, 16, 24, 26] and lay.total == 27
+    flat = np.arange(27, dtype=F32)
+    v = lay.views(flat)
+    assert v[0].shape == (4, 3) and v[2][1, 0] == 20 and v[4].shape == ()
+    v[1][...] = -1                                        # views alias the flat buffer
+    assert np.all(flat[12:16] == -1)
+    assert shard_rows(8192, 3, 8) == (3072, 4096)
+    with pytest.raises(ValueError):
+        shard_rows(10, 0, 4)
+
+
+def test_two_rank_step_matches_single_process():
+    import torch.multiprocessing as mp
+
+    import oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process full-batch reference
+    rng = np.random.default_rng(0)
+    sizes = [12, 16, 5]
+    params = []
+    for i, o in zip(sizes[:-1], sizes[1:]):
+        k = 1 / np.sqrt(i)
+        params.append((O.uniform_init(rng, (o, i), k), O.uniform_init(rng, (o,), k)))
+    x = rng.uniform(-1, 1, (8, sizes[0])).astype(F32)
+    t = np.eye(sizes[-1], dtype=F32)[rng.integers(0, sizes[-1], 8)]
+    O.mlp_step(x, t, params, lr=0.1)
+    want = [p for wb in params for p in wb]
+    # mean-reduced loss: the average of the two shard gradients equals the full-batch gradient
+    for a, b in zip(got, want):
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-7)

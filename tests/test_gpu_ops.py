@@ -481,3 +481,32 @@ def test_conv2d_tensor_core_forward(nk, dev, O, shape, cout, k):
     finally:
         del os.environ["NK_CONV_DIRECT"]
     assert np.all(np.abs(yd.as_ndarray() - y.as_ndarray()) <= 2e-3 * scale + 2.0 ** -7 * np.abs(want))
+
+
+@pytest.mark.parametrize("shape,cout,k", [((2, 3, 20, 24), 64, (3, 3)), ((1, 3, 224, 224), 64, (3, 3)),
+                                          ((3, 8, 17, 40), 32, (3, 3)), ((2, 5, 9, 72), 100, (2, 3)),
+                                          ((2, 32, 12, 32), 64, (3, 3)), ((2, 4, 6, 16), 8, (4, 1))])
+def test_conv2d_tensor_core_backward_kernel(nk, dev, O, shape, cout, k):
+    """dW (+ fused dbias) on the tcgen05 engine: G and x read once, accumulate-into-grad protocol (beta = 1)"""
+    from neuronika_b200 import ops
+    rng = np.random.default_rng(12)
+    x = O.bf16_round(rnd(rng, shape, 0, 1))
+    ho, wo = shape[2] - k[0] + 1, shape[3] - k[1] + 1
+    g = O.bf16_round(rnd(rng, (shape[0], cout, ho, wo)))
+    w0 = rnd(rng, (cout, shape[1]) + k)
+    b0 = rnd(rng, (cout, 1, 1))
+    dw = dev.from_ndarray(w0, nk.F32)
+    db = dev.from_ndarray(b0, nk.F32)
+    ops.conv2d_bwd_kernel(dw, dev.from_ndarray(g, nk.BF16), dev.from_ndarray(x, nk.BF16), beta=1.0, dbias=db)
+    # wide inputs (Cin*kh*kw*16/9 > 256 accumulator columns) fall back to the direct engine: same contract
+    assert dev.last_conv_kernel == ("tcgen05_implicit_gemm_dw" if shape[1] <= 20 else "direct_bwd_kernel")
+    want = np.zeros_like(w0, dtype=np.float32)
+    O.conv_backward_kernel(want, g, x, (1, 1), (1, 1))
+    scale = float(np.sqrt((want.astype(np.float64) ** 2).mean())) + 1e-9
+    assert np.all(np.abs(dw.as_ndarray() - (w0 + want)) <= 2e-3 * scale + 1e-5), float(np.abs(dw.as_ndarray() - (w0 + want)).max())
+    wb = g.astype(np.float64).sum((0, 2, 3)).reshape(cout, 1, 1)
+    assert np.all(np.abs(db.as_ndarray() - (b0 + wb)) <= 2e-3 * (np.abs(wb).max() + 1) + 1e-4)
+    # overwrite mode (beta = 0) and bf16 gradient storage
+    dwb = dev.from_ndarray(w0, nk.BF16)
+    ops.conv2d_bwd_kernel(dwb, dev.from_ndarray(g, nk.BF16), dev.from_ndarray(x, nk.BF16), beta=0.0)
+    assert np.all(np.abs(dwb.as_ndarray() - want) <= 2e-3 * scale + 2.0 ** -8 * np.abs(want) + 1e-5)
