@@ -138,6 +138,7 @@ def run_own(args):
 
     import neuronika_b200 as nk
     from neuronika_b200 import variable as V
+    from neuronika_b200.parallel import GradientBucket
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -159,14 +160,10 @@ def run_own(args):
 
     # ---- parameters with gradients in ONE contiguous bucket (single all-reduce)
     def make_bucket(shapes):
-        total = sum(int(np.prod(s)) for s in shapes)
-        bucket = nk.CuArray(dev, (total,), gdt)
-        views, off = [], 0
-        for s in shapes:
-            n = int(np.prod(s))
-            views.append(bucket.slice_flat(off, s))
-            off += n
-        return bucket, views
+        if world == 1:      # no exchange step: let the graph own (and lazily clear) the gradients
+            return None, [None] * len(shapes)
+        b = GradientBucket(dev, shapes, gdt)
+        return b, b.views
 
     def param(values, grad_view):
         return V.from_ndarray(dev, values, BF).requires_grad(gdt, grad_view)
@@ -271,12 +268,9 @@ def run_own(args):
             loss.backward(1.0)
         roots = (y, loss)
 
-    bucket_t = as_torch(bucket, torch, local) if world > 1 else None
-
     def exchange_and_update():
         if world > 1:
-            with torch.cuda.stream(stream):
-                dist.all_reduce(bucket_t)
+            bucket.all_reduce(stream)
         if opt is not None:
             opt.step()
 
@@ -329,6 +323,14 @@ def run_own(args):
 
     W_ = max(args.warmup, 3)
     ms, launches, clocks = timed(lambda: full_step(step_resident), args.steps, W_, sample_clocks=True)
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "profile_only": True, "ms_per_step": round(ms / args.steps, 5),
+                              "gpu_launches": int(launches), "workload": spec["name"]}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
     ms_e2e, _, _ = timed(e2e_step, e2e_steps, 3)
 
@@ -506,6 +508,8 @@ def main():
     ap.add_argument("--master-weights", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--profile", action="store_true",
+                    help="only the warm-up + timed steps (no e2e / roofline / cpu legs): for ncu launch lists")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -23,10 +23,6 @@
 #include "nk_internal.cuh"
 #include "nk_ptx.cuh"
 
-int nk_conv2d_bwd_input_tc(nk_ctx*, void*, const void*, const void*, int64_t, int64_t, int64_t, int64_t, int64_t,
-                           int64_t, int64_t, float) {
-  return NK_ERR_UNSUPPORTED;
-}
 
 namespace {
 
@@ -64,6 +60,32 @@ __device__ __forceinline__ uint32_t sw128_word(int r, int w) {
 // TMA can only start a box on a 16-byte boundary (profiles/r01_tma_alignment_probe.md), so the horizontal taps
 // j >= 1 are produced here: out[px] = in[px + j] for the R live K-rows of each chunk, reading the tap-0 window
 // (swizzled, written by TMA) plus the 8-pixel halo box, writing the swizzled tap-j slot.
+// kw <= 3 fast path: one warp instruction moves TWO K-rows (lanes 0-15 / 16-31), 8 bytes per lane
+__device__ __forceinline__ void shift_taps_kw3(uint8_t* stage_ptr, int kw, int R, int t) {
+  const uint8_t* halo = stage_ptr + kw * kSlotBytes;
+  const int lane = t & 31, wrp = t >> 5, l16 = lane & 15, sub = lane >> 4;
+  const int pairs = (R + 1) >> 1;
+  for (int c = 0; c < kChunksPerTile; ++c)
+    for (int pr = wrp; pr < pairs; pr += kShiftThreads / 32) {
+      const int r = pr * 2 + sub;
+      const bool live = r < R;
+      const int rr = live ? r : 0;
+      // words 2*l16, 2*l16+1 of the row: same 16-byte chunk, so the pair stays contiguous under the swizzle
+      const uint32_t off = c * 2048 + sw128_word(rr, 2 * l16);
+      const uint2 own = *reinterpret_cast<const uint2*>(stage_ptr + off);
+      const uint32_t h0 = *reinterpret_cast<const uint32_t*>(halo + c * 256 + rr * 16);
+      uint32_t n0 = __shfl_down_sync(0xffffffffu, own.x, 1);  // word 2*l16 + 2 lives in the next lane
+      if (l16 == 15) n0 = h0;
+      if (live) {
+        uint2 o1;
+        o1.x = __funnelshift_r(own.x, own.y, 16);
+        o1.y = __funnelshift_r(own.y, n0, 16);
+        *reinterpret_cast<uint2*>(stage_ptr + kSlotBytes + off) = o1;
+        if (kw > 2) *reinterpret_cast<uint2*>(stage_ptr + 2 * kSlotBytes + off) = make_uint2(own.y, n0);
+      }
+    }
+}
+
 __device__ __forceinline__ void shift_taps(uint8_t* stage_ptr, int kw, int R, int t) {
   const uint8_t* halo = stage_ptr + kw * kSlotBytes;
   const int lane = t & 31, wrp = t >> 5;
@@ -102,7 +124,8 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   const uint32_t stage_bytes = p.kw * kSlotBytes + kHaloBytes;
   const uint32_t st_off = p.kblocks * 16384;
   const uint32_t sg_off = st_off + p.stages * stage_bytes;
-  const uint32_t bar_off = sg_off + kChunksPerTile * rows * 128;
+  const uint32_t sg_bytes = kChunksPerTile * rows * 128;
+  const uint32_t bar_off = sg_off + 2 * sg_bytes;
   const uint32_t bar_base = base + bar_off;
   const int S = p.stages;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -168,7 +191,7 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         const int n = tile / p.tiles_per_img;
         const int g0 = (tile - n * p.tiles_per_img) * kChunksPerTile;
         for (int grp = 0; grp < p.ng; ++grp) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
           ptx::mbar_expect_tx(full_bar(stage), tx);
           const uint32_t sb = base + st_off + stage * stage_bytes;
 #pragma unroll
@@ -231,7 +254,10 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int grp = 0; grp < p.ng; ++grp) {
         ptx::mbar_wait(full_bar(stage), phase);
-        shift_taps(base_ptr + st_off + stage * stage_bytes, p.kw, p.R, t);
+        if (p.kw <= 3)
+          shift_taps_kw3(base_ptr + st_off + stage * stage_bytes, p.kw, p.R, t);
+        else
+          shift_taps(base_ptr + st_off + stage * stage_bytes, p.kw, p.R, t);
         ptx::fence_proxy_async();  // these generic-proxy writes are read by the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ready_bar(stage));
@@ -252,11 +278,15 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     int as = 0;
     uint32_t aphase = 0;
     const int64_t plane = int64_t(p.ho) * p.wo;
-    uint8_t* sg = base_ptr + sg_off;
+    int buf = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n = tile / p.tiles_per_img;
       const int g0 = (tile - n * p.tiles_per_img) * kChunksPerTile;
-      ptx::mbar_wait(tmem_full_bar(as), aphase);
+      // double-buffered staging: the barrier of the previous tile separates this buffer's last readers (two
+      // tiles ago) from the writes below
+      uint8_t* sg = base_ptr + sg_off + buf * sg_bytes;
+      buf ^= 1;
+      ptx::mbar_wait_relaxed(tmem_full_bar(as), aphase);
       ptx::tc_fence_after();
       if (q * 32 < rows) {
 #pragma unroll 1
@@ -347,7 +377,6 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
           }
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // staging buffer free again
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
@@ -412,7 +441,7 @@ int nk_conv2d_fwd_tc(nk_ctx* ctx, void* y, const void* x, const void* w, const v
   p.relu = relu;
   const int rows = (p.cout + 31) & ~31;
   const size_t stage_bytes = size_t(p.kw) * kSlotBytes + kHaloBytes;
-  const size_t fixed = 1024 + size_t(p.kblocks) * 16384 + size_t(kChunksPerTile) * rows * 128 + 512;
+  const size_t fixed = 1024 + size_t(p.kblocks) * 16384 + 2 * size_t(kChunksPerTile) * rows * 128 + 512;
   if (fixed + 2 * stage_bytes > 232448) return NK_ERR_UNSUPPORTED;
   p.stages = int((232448 - fixed) / stage_bytes);
   if (p.stages > 6) p.stages = 6;
@@ -462,9 +491,9 @@ constexpr int kWProducers = 128;
 
 struct ConvWP {
   int n, cin, h, w, cout, kh, kw, ho, wo;
-  int cpr, chunks_per_img;
-  long long total_chunks, chunks_per_cta;
-  int cpg, ng, ksteps, ncols, stages, fuse_dbias, R;
+  int cpr, chunks_per_img, tiles_per_img;
+  long long total_tiles, tiles_per_cta;
+  int cpg, ng, ksteps, ncols, stages, fuse_dbias, R, cout_pad, nacc;
   uint32_t tmem_cols;
   const __nv_bfloat16* g;
   float* scratch;
@@ -477,9 +506,11 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
+  // a tile = 4 chunks of 64 pixels; per chunk: [G slot cout_pad x 128 B][X slots ksteps x 16 x 128 B][halo ng x 256 B]
+  const uint32_t g_bytes = p.cout_pad * 128;
   const uint32_t x_bytes = p.ksteps * 2048;
-  const uint32_t halo_off = 16384 + x_bytes;
-  const uint32_t stage_bytes = halo_off + 1024;  // [G tile 128 x 128 B][X slots ksteps x 16 x 128 B][halo ng x 256 B]
+  const uint32_t chunk_bytes = g_bytes + x_bytes + 1024;
+  const uint32_t stage_bytes = kChunksPerTile * chunk_bytes;
   const uint32_t bar_off = p.stages * stage_bytes;
   const uint32_t bar_base = base + bar_off;
   const int S = p.stages;
@@ -496,10 +527,12 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     for (uint32_t i = threadIdx.x; i < S * stage_bytes / 16; i += kWThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
-  if (p.fuse_dbias) {  // ones row: slot 0, row 15 (no box and no shift ever writes rows >= R, R <= 15 here)
-    for (int i = threadIdx.x; i < S * 32; i += kWThreads) {
-      const int s = i / 32, wq = i % 32;
-      *reinterpret_cast<uint32_t*>(base_ptr + s * stage_bytes + 16384 + 15 * 128 + wq * 4) = 0x3F803F80u;
+  if (p.fuse_dbias) {  // ones row: X slot 0, row 15 of every chunk (no box and no shift writes rows >= R, R <= 15)
+    for (int i = threadIdx.x; i < S * kChunksPerTile * 32; i += kWThreads) {
+      const int sc = i / 32, wq = i % 32;
+      const int s = sc / kChunksPerTile, c = sc % kChunksPerTile;
+      *reinterpret_cast<uint32_t*>(base_ptr + s * stage_bytes + c * chunk_bytes + g_bytes + 15 * 128 + wq * 4) =
+          0x3F803F80u;
     }
   }
   if (warp_idx == 0 && lane == 0) {
@@ -523,26 +556,33 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const long long ch_begin = (long long)blockIdx.x * p.chunks_per_cta;
-  long long ch_end = ch_begin + p.chunks_per_cta;
-  if (ch_end > p.total_chunks) ch_end = p.total_chunks;
+  const long long t_begin = (long long)blockIdx.x * p.tiles_per_cta;
+  long long t_end = t_begin + p.tiles_per_cta;
+  if (t_end > p.total_tiles) t_end = p.total_tiles;
 
   if (warp_idx == 0) {
-    if (lane == 0) {  // TMA: tap-0 windows of every channel group + their 8-pixel halos
+    if (lane == 0) {  // TMA: tap-0 windows of every channel group + their 8-pixel halos, 4 chunks per stage
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx = uint32_t(p.ng) * (64u + 8u) * 2u * p.R;
-      for (long long ch = ch_begin; ch < ch_end; ++ch) {
-        const int n = int(ch / p.chunks_per_img);
-        const int g = int(ch - (long long)n * p.chunks_per_img);
-        const int prow = g / p.cpr, q0 = (g - prow * p.cpr) * kChunk;
-        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t tx = uint32_t(kChunksPerTile) * p.ng * (64u + 8u) * 2u * p.R;
+      for (long long tl = t_begin; tl < t_end; ++tl) {
+        const int n = int(tl / p.tiles_per_img);
+        const int g0 = int(tl - (long long)n * p.tiles_per_img) * kChunksPerTile;
+        ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
         ptx::mbar_expect_tx(fullx_bar(stage), tx);
-        const uint32_t sx = base + stage * stage_bytes + 16384;
-        for (int grp = 0; grp < p.ng; ++grp) {
-          ptx::tma_load_4d(sx + grp * 2048, &tmap_x, fullx_bar(stage), q0, prow, grp * p.cpg, n);
-          ptx::tma_load_4d(base + stage * stage_bytes + halo_off + grp * 256, &tmap_halo, fullx_bar(stage), q0 + kChunk,
-                           prow, grp * p.cpg, n);
+        for (int c = 0; c < kChunksPerTile; ++c) {
+          const int g = g0 + c;
+          int prow = p.h, q0 = 0;  // out of range chunk: zero fill
+          if (g < p.chunks_per_img) {
+            prow = g / p.cpr;
+            q0 = (g - prow * p.cpr) * kChunk;
+          }
+          const uint32_t sc = base + stage * stage_bytes + c * chunk_bytes;
+          for (int grp = 0; grp < p.ng; ++grp) {
+            ptx::tma_load_4d(sc + g_bytes + grp * 2048, &tmap_x, fullx_bar(stage), q0, prow, grp * p.cpg, n);
+            ptx::tma_load_4d(sc + g_bytes + x_bytes + grp * 256, &tmap_halo, fullx_bar(stage), q0 + kChunk, prow,
+                             grp * p.cpg, n);
+          }
         }
         if (++stage == S) {
           stage = 0;
@@ -555,20 +595,26 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const uint32_t idesc = ptx::make_idesc_bf16(128, p.ncols, false, false);
       int stage = 0;
       uint32_t phase = 0;
-      bool first = true;
-      for (long long ch = ch_begin; ch < ch_end; ++ch) {
+      // Each UMMA here is tiny (N = ncols <= 64 columns, ~24 tensor cycles) and they all accumulate: issued into ONE
+      // accumulator they serialise on the accumulate latency (measured 1.35 ms at config 3).  Round-robin over
+      // `nacc` independent accumulators (summed in the epilogue) keeps the tensor pipe busy.
+      uint32_t started = 0;  // bit a set once accumulator a has been written
+      for (long long tl = t_begin; tl < t_end; ++tl) {
         ptx::mbar_wait(ready_bar(stage), phase);
         ptx::fence_proxy_async();  // cp.async / st.shared (generic proxy) writes -> async proxy (UMMA)
         ptx::tc_fence_after();
-        const uint32_t sa = base + stage * stage_bytes;
-        const uint64_t adesc = ptx::make_smem_desc_sw128(sa, 16, 1024);
-        const uint64_t bdesc = ptx::make_smem_desc_sw128(sa + 16384, 16, 1024);
+        for (int c = 0; c < kChunksPerTile; ++c) {
+          const uint32_t sc = base + stage * stage_bytes + c * chunk_bytes;
+          const uint64_t adesc = ptx::make_smem_desc_sw128(sc, 16, 1024);
+          const uint64_t bdesc = ptx::make_smem_desc_sw128(sc + g_bytes, 16, 1024);
 #pragma unroll
-        for (int kq = 0; kq < 4; ++kq) {
-          ptx::mma_f16_ss(tmem_base, adesc + uint64_t(kq * 2), bdesc + uint64_t(kq * 2), idesc,
-                          (first && kq == 0) ? 0u : 1u);
+          for (int kq = 0; kq < 4; ++kq) {
+            const uint32_t a = uint32_t(c * 4 + kq) & uint32_t(p.nacc - 1);
+            ptx::mma_f16_ss(tmem_base + a * uint32_t(p.ncols), adesc + uint64_t(kq * 2), bdesc + uint64_t(kq * 2), idesc,
+                            (started >> a) & 1u);
+            started |= 1u << a;
+          }
         }
-        first = false;
         ptx::mma_commit(empty_bar(stage));
         if (++stage == S) {
           stage = 0;
@@ -578,46 +624,48 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       ptx::mma_commit(done_bar);
     }
   } else {
-    // ---- producers: cp.async G rows into the swizzled K-major A tile, then build the taps j >= 1 of the B tile
+    // ---- producers: cp.async G rows into the swizzled K-major A slots, then build the taps j >= 1 of the B slots
     const int t = threadIdx.x - 64;  // 0..127
+    const int piece = t & 31, co0 = t >> 5, wrp = t >> 5;
+    const uint32_t sw0 = (((piece >> 2) ^ (co0 & 7)) << 4) + (piece & 3) * 4;
+    const uint32_t sw1 = (((piece >> 2) ^ ((co0 + 4) & 7)) << 4) + (piece & 3) * 4;
     int stage = 0;
     uint32_t phase = 0;
     const long long plane = (long long)p.ho * p.wo;
-    for (long long ch = ch_begin; ch < ch_end; ++ch) {
-      const int n = int(ch / p.chunks_per_img);
-      const int g = int(ch - (long long)n * p.chunks_per_img);
-      const int prow = g / p.cpr, q0 = (g - prow * p.cpr) * kChunk;
-      const int valid = min(kChunk, p.wo - q0);
-      ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-      const uint32_t sa = base + stage * stage_bytes;
+    for (long long tl = t_begin; tl < t_end; ++tl) {
+      const int n = int(tl / p.tiles_per_img);
+      const int g0 = int(tl - (long long)n * p.tiles_per_img) * kChunksPerTile;
+      ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
       uint8_t* sp = base_ptr + stage * stage_bytes;
-      const __nv_bfloat16* gsrc = p.g + (long long)n * p.cout * plane + (long long)prow * p.wo + q0;
-      {
-        // thread t owns 4-byte piece (t & 31) of rows (t >> 5), (t >> 5) + 4, ...: everything but the row
-        // base is loop invariant, and (co & 7) only alternates between two values
-        const int piece = t & 31, co0 = t >> 5;
+      const uint32_t sa = base + stage * stage_bytes;
+      int prow = g0 / p.cpr, qc = g0 - prow * p.cpr;
+      for (int c = 0; c < kChunksPerTile; ++c, ++qc) {
+        if (qc == p.cpr) {
+          qc = 0;
+          ++prow;
+        }
+        const bool live = g0 + c < p.chunks_per_img;
+        const int q0 = qc * kChunk;
+        const int valid = live ? min(kChunk, p.wo - q0) : 0;
         int nbytes = (valid - piece * 2) * 2;
         nbytes = nbytes < 0 ? 0 : (nbytes > 4 ? 4 : nbytes);
-        const __nv_bfloat16* src = gsrc + (long long)co0 * plane + (nbytes ? piece * 2 : 0);
-        const long long sstep = 4 * plane;
-        const uint32_t sw0 = (((piece >> 2) ^ (co0 & 7)) << 4) + (piece & 3) * 4;
-        const uint32_t sw1 = (((piece >> 2) ^ ((co0 + 4) & 7)) << 4) + (piece & 3) * 4;
-        uint32_t drow = sa + co0 * 128;
-        for (int co = co0, it = 0; co < p.cout; co += 4, ++it, src += sstep, drow += 512) {
+        const __nv_bfloat16* src = p.g + (long long)n * p.cout * plane + (long long)co0 * plane +
+                                   (nbytes ? (long long)prow * p.wo + q0 + piece * 2 : 0);
+        uint32_t drow = sa + c * chunk_bytes + co0 * 128;
+        for (int co = co0, it = 0; co < p.cout; co += 4, ++it, src += 4 * plane, drow += 512) {
           const uint32_t dst = drow + ((it & 1) ? sw1 : sw0);
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
         }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ready_bar(stage)) : "memory");
       // taps: slot(j*ng + grp)[r][px] = slot(grp)[r][px + j]   (tap-0 window + 8-pixel halo, see shift_taps)
-      ptx::mbar_wait(fullx_bar(stage), phase);
-      {
-        const uint8_t* halo = sp + halo_off;
-        const int wrp = t >> 5;
+      ptx::mbar_wait_relaxed(fullx_bar(stage), phase);
+      for (int c = 0; c < kChunksPerTile; ++c) {
+        uint8_t* xs = sp + c * chunk_bytes + g_bytes;
+        const uint8_t* halo = xs + x_bytes;
         for (int grp = 0; grp < p.ng; ++grp)
           for (int r = wrp; r < p.R; r += kWProducers / 32) {
-            const uint8_t* raw = sp + 16384 + grp * 2048;
-            const uint32_t own = *reinterpret_cast<const uint32_t*>(raw + sw128_word(r, lane));
+            const uint32_t own = *reinterpret_cast<const uint32_t*>(xs + grp * 2048 + sw128_word(r, lane));
             const uint32_t hl = *reinterpret_cast<const uint32_t*>(halo + grp * 256 + r * 16 + (lane & 3) * 4);
             const uint32_t doff = sw128_word(r, lane);
             for (int j = 1; j < p.kw; ++j) {
@@ -628,7 +676,7 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               if (i0 >= 32) lo = h0;
               if (i1 >= 32) hi = h1;
               const uint32_t out = (j & 1) ? __funnelshift_r(lo, hi, 16) : lo;
-              *reinterpret_cast<uint32_t*>(sp + 16384 + (j * p.ng + grp) * 2048 + doff) = out;
+              *reinterpret_cast<uint32_t*>(xs + (j * p.ng + grp) * 2048 + doff) = out;
             }
           }
       }
@@ -643,17 +691,26 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // ---- epilogue: one pass of atomics per CTA
     ptx::mbar_wait(done_bar, 0);
     ptx::tc_fence_after();
-    if (ch_end > ch_begin) {
+    if (t_end > t_begin) {
       const int q = warp_idx & 3;
       const int co = q * 32 + lane;
       if (q * 32 < p.cout) {
+        const long long ntiles = t_end - t_begin;
+        const int live_acc = ntiles * 16 < p.nacc ? int(ntiles * 16) : p.nacc;  // accumulators that were written
         for (int c0 = 0; c0 < p.ncols; c0 += 16) {
-          uint32_t r[16];
-          ptx::tmem_ld_32x32b_x16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c0), r);
-          ptx::tmem_ld_wait();
+          float sum[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) sum[jj] = 0.f;
+          for (int a = 0; a < live_acc; ++a) {
+            uint32_t r[16];
+            ptx::tmem_ld_32x32b_x16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(a * p.ncols + c0), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) sum[jj] += __uint_as_float(r[jj]);
+          }
           if (co < p.cout) {
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) atomicAdd(&p.scratch[co * p.ncols + c0 + jj], __uint_as_float(r[jj]));
+            for (int jj = 0; jj < 16; ++jj) atomicAdd(&p.scratch[co * p.ncols + c0 + jj], sum[jj]);
           }
         }
       }
@@ -711,18 +768,22 @@ int nk_conv2d_bwd_kernel_tc(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, c
   p.ncols = p.ksteps * 16;
   if (p.ncols > 256 || p.ng > 4) return NK_ERR_UNSUPPORTED;
   p.fuse_dbias = (dbias != nullptr && p.kh * p.cpg < 16) ? 1 : 0;
-  p.tmem_cols = p.ncols <= 32 ? 32 : p.ncols <= 64 ? 64 : p.ncols <= 128 ? 128 : 256;
+  p.nacc = p.ncols <= 32 ? 16 : p.ncols <= 64 ? 8 : p.ncols <= 128 ? 4 : 2;
+  p.tmem_cols = 512;
   p.cpr = (p.wo + kChunk - 1) / kChunk;
   p.chunks_per_img = p.ho * p.cpr;
-  p.total_chunks = (long long)p.n * p.chunks_per_img;
-  const uint32_t stage_bytes = 16384 + p.ksteps * 2048 + 1024;
-  p.stages = int((232448 - 2048) / stage_bytes);
-  if (p.stages > 8) p.stages = 8;
+  p.tiles_per_img = (p.chunks_per_img + kChunksPerTile - 1) / kChunksPerTile;
+  p.total_tiles = (long long)p.n * p.tiles_per_img;
+  p.cout_pad = (p.cout + 7) & ~7;
+  const uint32_t stage_bytes = kChunksPerTile * (p.cout_pad * 128 + p.ksteps * 2048 + 1024);
+  // + 16 KB tail: the M = 128 UMMA reads 128 A rows although only cout_pad are loaded (lanes >= Cout are unused)
+  p.stages = int((232448 - 2048 - 16384) / stage_bytes);
+  if (p.stages > 4) p.stages = 4;
   if (p.stages < 2) return NK_ERR_UNSUPPORTED;
   int grid = ctx->sm_count;
-  if (p.total_chunks < grid) grid = (int)p.total_chunks;
-  p.chunks_per_cta = (p.total_chunks + grid - 1) / grid;
-  grid = int((p.total_chunks + p.chunks_per_cta - 1) / p.chunks_per_cta);
+  if (p.total_tiles < grid) grid = (int)p.total_tiles;
+  p.tiles_per_cta = (p.total_tiles + grid - 1) / grid;
+  grid = int((p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta);
   p.g = static_cast<const __nv_bfloat16*>(g);
   float* scratch;
   int rc = nk_workspace(ctx, size_t(128) * p.ncols * sizeof(float), (void**)&scratch);
@@ -748,7 +809,7 @@ int nk_conv2d_bwd_kernel_tc(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, c
     NK_CUDA(ctx, cudaFuncSetAttribute(conv_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_done = true;
   }
-  const size_t smem = 1024 + size_t(p.stages) * stage_bytes + 512;
+  const size_t smem = 1024 + size_t(p.stages) * stage_bytes + 512 + 16384;
   conv_dw_tc_kernel<<<grid, kWThreads, smem, ctx->stream>>>(tm, tmh, p);
   NK_LAUNCHED(ctx, "conv_dw_tc");
   const int total = int(cout * cin * kh * kw + cout);
@@ -759,5 +820,321 @@ int nk_conv2d_bwd_kernel_tc(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, c
     conv_dw_finalize<float><<<blocks, 256, 0, ctx->stream>>>((float*)dwt, (float*)dbias, scratch, p.cout, p.cin, p.kh, p.kw, p.cpg, p.ng, p.ncols, beta, p.fuse_dbias);
   NK_LAUNCHED(ctx, "conv_dw_finalize");
   ctx->last_conv_kernel = "tcgen05_implicit_gemm_dw";
+  return NK_OK;
+}
+
+
+// =====================================================================================================
+// dX: dx[n,c,u,v] += sum_{o,i,j} G[n,o,u-i,v-j] * W[o,c,i,j]      (convolution/mod.rs:146-189, intended maths)
+//
+// The reference builds the (N, K, L) column buffer with one sgemm per sample and scatters it back with
+// overlapping strided adds (col2im).  Here, per output-gradient row (n, p):
+//   D[m = (c,i,j)][px] = sum_o Wt[m][o] * G[o][px]        one UMMA chain, M = Cin*kh*kw (<= 32), N = 256 pixels,
+//                                                          K = Cout; B = the G row tile exactly as it lies in memory
+//   col2im in registers: thread v (one dx column) sums D[(c,i,j)][v-j] over j and keeps a kh-deep ring of partial
+//   dx rows; after G row p, dx row u = p is complete and is written once (coalesced along W).
+// G is read exactly once (cp.async: its 2*Wo-byte row pitch is not TMA-addressable), dx is written exactly once.
+// A CTA owns blocks of dx rows of one image and recomputes the kh-1 halo rows of G at a block boundary.
+// =====================================================================================================
+namespace {
+
+constexpr int kXThreads = 448;  // warp 0: TMEM reader, warp 1: MMA + TMEM alloc, warps 2..5: cp.async (G), warps 6..13: pixels
+constexpr int kXProducers = 128;
+constexpr int kSRowFloats = 260;  // padded row of the f32 exchange buffer (conflict-free 16-byte writes per lane)
+
+struct ConvXP {
+  int n, cin, h, w, cout, ho, wo;
+  int rb, blocks_per_img, num_units, stages, kblocks;
+  const __nv_bfloat16* g;
+  const __nv_bfloat16* wt;
+  __nv_bfloat16* dx;
+  float beta;
+};
+
+template <int CIN, int KH, int KW>
+__global__ void __launch_bounds__(kXThreads, 1) conv_dx_tc_kernel(const ConvXP p) {
+  constexpr int M = CIN * KH * KW;
+  static_assert(M <= 32, "the (c,i,j) rows must fit one TMEM lane quarter");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_u32);
+  // layout: [weights kblocks x 16 KB][stages x (4 chunks x Cout rows x 128 B)][S: 2 x 32 rows x 1040 B][barriers]
+  const uint32_t chunk_bytes = p.cout * 128;
+  const uint32_t stage_bytes = kChunksPerTile * chunk_bytes;
+  const uint32_t st_off = p.kblocks * 16384;
+  const uint32_t s_off = st_off + p.stages * stage_bytes;
+  const uint32_t s_bytes = 32 * kSRowFloats * 4;
+  const uint32_t bar_off = s_off + 2 * s_bytes;
+  const uint32_t bar_base = base + bar_off;
+  const int S = p.stages;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * S + 2 + s); };
+  auto s_full_bar = [&](int s) { return bar_base + 8u * (2 * S + 4 + s); };
+  auto s_empty_bar = [&](int s) { return bar_base + 8u * (2 * S + 6 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * S + 8);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (2 * S + 8));
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  {
+    uint4* z = reinterpret_cast<uint4*>(base_ptr);
+    for (uint32_t i = threadIdx.x; i < s_off / 16; i += kXThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  {
+    // A[m][o] = W[o][c][i][j], m = (c*KH + i)*KW + j ; K-major SWIZZLE_128B tiles of 64 output channels
+    for (int idx = threadIdx.x; idx < p.cout * M; idx += kXThreads) {
+      const int o = idx / M, m = idx - o * M;
+      const int blk = o >> 6, col = o & 63;
+      const uint32_t off = blk * 16384 + m * 128 + (((col >> 3) ^ (m & 7)) << 4) + (col & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(base_ptr + off) = p.wt[idx];
+    }
+  }
+  if (warp_idx == 0 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(full_bar(s), kXProducers);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tmem_full_bar(s), 1);
+      ptx::mbar_init(tmem_empty_bar(s), 1);
+      ptx::mbar_init(s_full_bar(s), 1);
+      ptx::mbar_init(s_empty_bar(s), 8);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // every role walks the same sequence of (unit, G row) tiles
+  auto unit_rows = [&](int unit, int& n, int& u0, int& u1, int& p_lo, int& p_hi) {
+    n = unit / p.blocks_per_img;
+    const int b = unit - n * p.blocks_per_img;
+    u0 = b * p.rb;
+    u1 = min(u0 + p.rb, p.h);
+    p_lo = max(0, u0 - (KH - 1));
+    p_hi = min(p.ho, u1) - 1;
+  };
+
+  if (warp_idx == 1) {
+    if (lane == 0) {  // ===================================================== MMA issuer
+      const uint32_t idesc = ptx::make_idesc_bf16(128, 256, false, true);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        int n, u0, u1, p_lo, p_hi;
+        unit_rows(unit, n, u0, u1, p_lo, p_hi);
+        for (int pr = p_lo; pr <= p_hi; ++pr) {
+          ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1u);
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::fence_proxy_async();
+          ptx::tc_fence_after();
+          const uint32_t sb = base + st_off + stage * stage_bytes;
+          const uint32_t tmem_d = tmem_base + uint32_t(as * 256);
+          for (int ks = 0; ks < p.cout / 16; ++ks) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(base + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + ks * 2048, chunk_bytes, 1024);
+            ptx::mma_f16_ss(tmem_d, adesc, bdesc, idesc, ks != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(empty_bar(stage));
+          ptx::mma_commit(tmem_full_bar(as));
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          as ^= 1;
+          if (as == 0) aphase ^= 1u;
+        }
+      }
+    }
+  } else if (warp_idx == 0) {
+    // ===================================================== TMEM reader: D rows (c,i,j) -> f32 exchange buffer
+    int as = 0, sbuf = 0;
+    uint32_t aphase = 0, sphase = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int n, u0, u1, p_lo, p_hi;
+      unit_rows(unit, n, u0, u1, p_lo, p_hi);
+      for (int pr = p_lo; pr <= p_hi; ++pr) {
+        ptx::mbar_wait(tmem_full_bar(as), aphase);
+        ptx::tc_fence_after();
+        ptx::mbar_wait(s_empty_bar(sbuf), sphase ^ 1u);
+        float* srow = reinterpret_cast<float*>(base_ptr + s_off + sbuf * s_bytes) + lane * kSRowFloats;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + uint32_t(as * 256 + c0), r);
+          ptx::tmem_ld_wait();
+          if (lane < M) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+              *reinterpret_cast<uint4*>(srow + c0 + v * 4) = make_uint4(r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(tmem_empty_bar(as));
+          ptx::mbar_arrive(s_full_bar(sbuf));
+        }
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+        sbuf ^= 1;
+        if (sbuf == 0) sphase ^= 1u;
+      }
+    }
+  } else if (warp_idx < 6) {
+    // ===================================================== producers: cp.async the G row (Cout x Wo) into the B tile
+    const int t = threadIdx.x - 64;
+    const int piece = t & 31, o0 = t >> 5;
+    int stage = 0;
+    uint32_t phase = 0;
+    const long long plane = (long long)p.ho * p.wo;
+    const uint32_t sw0 = (((piece >> 2) ^ (o0 & 7)) << 4) + (piece & 3) * 4;
+    const uint32_t sw1 = (((piece >> 2) ^ ((o0 + 4) & 7)) << 4) + (piece & 3) * 4;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int n, u0, u1, p_lo, p_hi;
+      unit_rows(unit, n, u0, u1, p_lo, p_hi);
+      for (int pr = p_lo; pr <= p_hi; ++pr) {
+        ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
+        const uint32_t sb = base + st_off + stage * stage_bytes;
+        const __nv_bfloat16* grow = p.g + (long long)n * p.cout * plane + (long long)pr * p.wo;
+#pragma unroll
+        for (int c = 0; c < kChunksPerTile; ++c) {
+          int nbytes = (p.wo - c * kChunk - piece * 2) * 2;
+          nbytes = nbytes < 0 ? 0 : (nbytes > 4 ? 4 : nbytes);
+          const __nv_bfloat16* src = grow + (long long)o0 * plane + (nbytes ? c * kChunk + piece * 2 : 0);
+          uint32_t drow = sb + c * chunk_bytes + o0 * 128;
+          for (int o = o0, it = 0; o < p.cout; o += 4, ++it, src += 4 * plane, drow += 512) {
+            const uint32_t dst = drow + ((it & 1) ? sw1 : sw0);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+          }
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(stage)) : "memory");
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================================================== pixel warps: col2im in registers, one dx column each
+    const int v = threadIdx.x - 6 * 32;  // 0..255
+    const bool col_live = v < p.w;
+    int sbuf = 0;
+    uint32_t sphase = 0;
+    const long long img = (long long)p.h * p.w;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int n, u0, u1, p_lo, p_hi;
+      unit_rows(unit, n, u0, u1, p_lo, p_hi);
+      float ring[CIN][KH];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int k = 0; k < KH; ++k) ring[c][k] = 0.f;
+      __nv_bfloat16* dxn = p.dx + (long long)n * CIN * img + v;
+      auto emit = [&](int u) {  // ring[.][0] holds the finished dx row u of every channel
+        if (u >= u0 && u < u1 && col_live) {
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            __nv_bfloat16* d = dxn + (long long)c * img + (long long)u * p.w;
+            float val = ring[c][0];
+            if (p.beta != 0.f) val += p.beta * __bfloat162float(*d);
+            *d = __float2bfloat16_rn(val);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+#pragma unroll
+          for (int k = 0; k + 1 < KH; ++k) ring[c][k] = ring[c][k + 1];
+          ring[c][KH - 1] = 0.f;
+        }
+      };
+      for (int pr = p_lo; pr <= p_hi; ++pr) {
+        ptx::mbar_wait_relaxed(s_full_bar(sbuf), sphase);
+        const float* Sb = reinterpret_cast<const float*>(base_ptr + s_off + sbuf * s_bytes);
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+#pragma unroll
+          for (int i = 0; i < KH; ++i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) {
+              const int q = v - j;
+              if (q >= 0) acc += Sb[((c * KH + i) * KW + j) * kSRowFloats + q];
+            }
+            ring[c][i] += acc;
+          }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(s_empty_bar(sbuf));
+        sbuf ^= 1;
+        if (sbuf == 0) sphase ^= 1u;
+        emit(pr);
+      }
+      // rows below the last G row (only the last block of an image has them)
+      for (int u = p_hi + 1; u < u1; ++u) emit(u);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int CIN>
+int launch_dx(nk_ctx* ctx, const ConvXP& p, int grid, size_t smem) {
+  auto kern = conv_dx_tc_kernel<CIN, 3, 3>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_done = true;
+  }
+  kern<<<grid, kXThreads, smem, ctx->stream>>>(p);
+  NK_LAUNCHED(ctx, "conv_dx_tc");
+  return NK_OK;
+}
+
+}  // namespace
+
+int nk_conv2d_bwd_input_tc(nk_ctx* ctx, void* dx, const void* g, const void* w, int64_t n, int64_t cin, int64_t h,
+                           int64_t wd, int64_t cout, int64_t kh, int64_t kw, float beta) {
+  if (getenv("NK_CONV_DIRECT")) return NK_ERR_UNSUPPORTED;
+  if (kh != 3 || kw != 3 || cin < 1 || cin > 3) return NK_ERR_UNSUPPORTED;       // (c,i,j) rows <= 32 TMEM lanes
+  if (cout % 16 != 0 || cout > 128 || wd > 256 || n > (1 << 20)) return NK_ERR_UNSUPPORTED;
+  ConvXP p;
+  p.n = (int)n, p.cin = (int)cin, p.h = (int)h, p.w = (int)wd, p.cout = (int)cout;
+  p.ho = int(h - kh + 1), p.wo = int(wd - kw + 1);
+  if ((p.wo & 1) || (reinterpret_cast<uintptr_t>(g) & 3)) return NK_ERR_UNSUPPORTED;  // 4-byte cp.async pieces
+  p.kblocks = (p.cout + 63) / 64;
+  const size_t stage_bytes = size_t(kChunksPerTile) * p.cout * 128;
+  const size_t fixed = 1024 + size_t(p.kblocks) * 16384 + 2 * 32 * kSRowFloats * 4 + 512;
+  if (fixed + 2 * stage_bytes > 232448) return NK_ERR_UNSUPPORTED;
+  p.stages = int((232448 - fixed) / stage_bytes);
+  if (p.stages > 4) p.stages = 4;
+  // blocks of dx rows: enough units to balance 148 SMs, large enough to amortise the kh-1 recomputed halo rows
+  p.rb = 56;
+  if (p.h < 2 * p.rb) p.rb = p.h;
+  p.blocks_per_img = (p.h + p.rb - 1) / p.rb;
+  p.num_units = p.n * p.blocks_per_img;
+  p.g = static_cast<const __nv_bfloat16*>(g);
+  p.wt = static_cast<const __nv_bfloat16*>(w);
+  p.dx = static_cast<__nv_bfloat16*>(dx);
+  p.beta = beta;
+  const size_t smem = fixed + size_t(p.stages) * stage_bytes;
+  const int grid = p.num_units < ctx->sm_count ? p.num_units : ctx->sm_count;
+  int rc = cin == 1 ? launch_dx<1>(ctx, p, grid, smem) : cin == 2 ? launch_dx<2>(ctx, p, grid, smem) : launch_dx<3>(ctx, p, grid, smem);
+  if (rc) return rc;
+  ctx->last_conv_kernel = "tcgen05_implicit_gemm_dx";
   return NK_OK;
 }

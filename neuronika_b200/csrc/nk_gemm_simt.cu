@@ -178,12 +178,148 @@ int launch(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K,
   return NK_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Skinny shapes of config 4's last layer (Linear 4096 -> 10): the (N,10) logits and their gradient have a
+// 20-byte row pitch that TMA cannot address, and 64x64 tiles waste >80 % of their work on them.  Both kernels are
+// HBM-bound on the large operand and read/write it exactly once.
+//   small-K  (NN, K <= 16):  dH = G . W        C[m][n] = sum_k A[m][k] * B[k][n]
+//   small-M  (TN, M <= 16):  dW = G^T . H      C[m][n] = sum_k A[k][m] * B[k][n]   (split over k, f32 atomics)
+// ------------------------------------------------------------------------------------------------------
+constexpr int kSkinnyMax = 16;
+
+template <typename TAB, typename TC>
+__global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
+                                                           TC* __restrict__ C, int64_t M, int64_t N, int K,
+                                                           int64_t lda, int64_t ldb, int64_t ldc, Epilogue ep) {
+  // block: 32 rows x 1024 columns; thread: 4 consecutive columns, all 32 rows
+  __shared__ float As[32][kSkinnyMax];
+  const int64_t m0 = int64_t(blockIdx.y) * 32;
+  const int64_t n = (int64_t(blockIdx.x) * 256 + threadIdx.x) * 4;
+  for (int i = threadIdx.x; i < 32 * kSkinnyMax; i += 256) {
+    const int r = i / kSkinnyMax, k = i - r * kSkinnyMax;
+    As[r][k] = (k < K && m0 + r < M) ? nk_to_f32<TAB>(A[(m0 + r) * lda + k]) : 0.f;
+  }
+  __syncthreads();
+  if (n >= N) return;
+  float b[kSkinnyMax][4];
+#pragma unroll
+  for (int k = 0; k < kSkinnyMax; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[k][j] = (k < K && n + j < N) ? nk_to_f32<TAB>(B[int64_t(k) * ldb + n + j]) : 0.f;
+  for (int r = 0; r < 32 && m0 + r < M; ++r) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < kSkinnyMax; ++k) {
+      const float a = As[r][k];  // zero for k >= K
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, b[k][j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < N) store_out<TC>(C, ldc, m0 + r, n + j, acc[j], ep);
+  }
+}
+
+template <typename TAB>
+__global__ void __launch_bounds__(128) gemm_small_m_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
+                                                           float* __restrict__ scratch, int M, int64_t N, int64_t K,
+                                                           int64_t lda, int64_t ldb, int64_t k_per_block) {
+  // block: 512 columns (thread: 4 consecutive), one slab of k; A rows staged 64 at a time
+  __shared__ float As[64][kSkinnyMax];
+  const int64_t n = (int64_t(blockIdx.x) * 128 + threadIdx.x) * 4;
+  const int64_t k_begin = int64_t(blockIdx.y) * k_per_block;
+  int64_t k_end = k_begin + k_per_block;
+  if (k_end > K) k_end = K;
+  float acc[kSkinnyMax][4];
+#pragma unroll
+  for (int m = 0; m < kSkinnyMax; ++m)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * kSkinnyMax; i += 128) {
+      const int r = i / kSkinnyMax, m = i - r * kSkinnyMax;
+      As[r][m] = (m < M && k0 + r < k_end) ? nk_to_f32<TAB>(A[(k0 + r) * lda + m]) : 0.f;
+    }
+    __syncthreads();
+    if (n < N) {
+      const int kk_end = int(k_end - k0 < 64 ? k_end - k0 : 64);
+      for (int kk = 0; kk < kk_end; ++kk) {
+        float bv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = (n + j < N) ? nk_to_f32<TAB>(B[(k0 + kk) * ldb + n + j]) : 0.f;
+#pragma unroll
+        for (int m = 0; m < kSkinnyMax; ++m) {
+          const float a = As[kk][m];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[m][j] = fmaf(a, bv[j], acc[m][j]);
+        }
+      }
+    }
+  }
+  if (n < N)
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < N) atomicAdd(&scratch[int64_t(m) * N + n + j], acc[m][j]);
+}
+
+template <typename TAB, typename TC>
+int launch_skinny(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                  const void* B, int64_t ldb, void* C, int64_t ldc, Epilogue ep, bool* handled) {
+  *handled = false;
+  if (!transA && !transB && K <= kSkinnyMax && K > 0 && N >= 256) {
+    dim3 grid((unsigned)((N + 1023) / 1024), (unsigned)((M + 31) / 32));
+    if (grid.y > 65535) return NK_OK;
+    gemm_small_k_kernel<TAB, TC><<<grid, 256, 0, ctx->stream>>>((const TAB*)A, (const TAB*)B, (TC*)C, M, N, (int)K, lda,
+                                                               ldb, ldc, ep);
+    NK_LAUNCHED(ctx, "gemm_small_k");
+    ctx->last_gemm_kernel = "simt_small_k";
+    *handled = true;
+    return NK_OK;
+  }
+  if (transA && !transB && M <= kSkinnyMax && N >= 256 && K >= 256) {
+    float* scratch;
+    int rc = nk_workspace(ctx, size_t(M) * size_t(N) * sizeof(float), (void**)&scratch);
+    if (rc) return rc;
+    NK_CUDA(ctx, cudaMemsetAsync(scratch, 0, size_t(M) * size_t(N) * sizeof(float), ctx->stream));
+    const int64_t gx = (N + 511) / 512;
+    int64_t gy = (2 * int64_t(ctx->sm_count) * 4 + gx - 1) / gx;
+    int64_t k_per_block = (K + gy - 1) / gy;
+    k_per_block = (k_per_block + 63) / 64 * 64;
+    gy = (K + k_per_block - 1) / k_per_block;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    gemm_small_m_kernel<TAB><<<grid, 128, 0, ctx->stream>>>((const TAB*)A, (const TAB*)B, scratch, (int)M, N, K, lda, ldb,
+                                                           k_per_block);
+    NK_LAUNCHED(ctx, "gemm_small_m");
+    int64_t blocks = (M * N + kThreads - 1) / kThreads;
+    splitk_reduce_kernel<TC><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>((TC*)C, scratch, M, N, ldc, 1, ep);
+    NK_LAUNCHED(ctx, "gemm_small_m_finalize");
+    ctx->last_gemm_kernel = "simt_small_m";
+    *handled = true;
+    return NK_OK;
+  }
+  return NK_OK;
+}
+
 }  // namespace
 
 int nk_gemm_simt(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
                  int64_t lda, const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype,
                  int c_dtype, const void* bias, int bias_dtype, int relu) {
   Epilogue ep{alpha, beta, bias, bias_dtype == NK_BF16, relu};
+  bool handled = false;
+  int rc;
+  if (ab_dtype == NK_F32 && c_dtype == NK_F32)
+    rc = launch_skinny<float, float>(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, ep, &handled);
+  else if (ab_dtype == NK_BF16 && c_dtype == NK_BF16)
+    rc = launch_skinny<__nv_bfloat16, __nv_bfloat16>(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, ep, &handled);
+  else if (ab_dtype == NK_BF16 && c_dtype == NK_F32)
+    rc = launch_skinny<__nv_bfloat16, float>(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, ep, &handled);
+  else
+    rc = launch_skinny<float, __nv_bfloat16>(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, ep, &handled);
+  if (rc || handled) return rc;
   ctx->last_gemm_kernel = "simt_64x64x16";
   if (ab_dtype == NK_F32 && c_dtype == NK_F32)
     return launch<float, float>(ctx, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, ep);

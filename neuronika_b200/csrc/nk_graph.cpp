@@ -93,6 +93,7 @@ struct Gradient {
   bool owned = true;
   bool enabled = true;   // false after no_grad()
   bool is_zero = true;   // content known to be all zeros -> first accumulate may overwrite
+  bool stale = false;    // logically zero but the memory has not been cleared yet (lazy zero_grad)
   std::shared_ptr<Gradient> alias;  // fusion: this gradient IS that gradient
   Gradient(nk_ctx* c, Shape s, int dt) : ctx(c), shape(std::move(s)), dtype(dt) {}
   ~Gradient() {
@@ -108,24 +109,38 @@ struct Gradient {
     if (!r->ptr) {
       ck(r->ctx, nk_alloc(r->ctx, size_t(r->n()) * esize(r->dtype), &r->ptr));
       r->is_zero = true;
+      r->stale = false;
+    }
+    if (r->stale) {  // a reader wants the zeros that zero_grad() promised
+      ck(r->ctx, nk_memset0(r->ctx, r->ptr, size_t(r->n()) * esize(r->dtype)));
+      r->stale = false;
     }
     return r->ptr;
   }
-  // beta for an accumulating write (0 when known zero), and mark the buffer as touched
-  float acc_beta() {
+  // pointer + beta for an accumulating write that covers the whole buffer: beta = 0 when the content is
+  // known to be zero (then stale memory is simply overwritten), and the buffer counts as touched afterwards
+  void* acc(float* beta) {
     Gradient* r = root();
-    float b = r->is_zero ? 0.f : 1.f;
+    if (!r->enabled || !r->ptr) get();
+    *beta = r->is_zero ? 0.f : 1.f;
     r->is_zero = false;
-    return b;
+    r->stale = false;
+    return r->ptr;
   }
   void zero() {
     Gradient* r = root();
-    if (r->ptr && !r->is_zero) ck(r->ctx, nk_memset0(r->ctx, r->ptr, size_t(r->n()) * esize(r->dtype)));
+    if (r->ptr && !r->is_zero) {
+      if (r->owned)
+        r->stale = true;  // owned memory: clear lazily (first full overwrite or first read)
+      else
+        ck(r->ctx, nk_memset0(r->ctx, r->ptr, size_t(r->n()) * esize(r->dtype)));  // caller-visible memory
+    }
     r->is_zero = true;
   }
   void fill(float v) {
     Gradient* r = root();
-    ck(r->ctx, nk_fill(r->ctx, get(), r->dtype, size_t(r->n()), v));
+    float unused;
+    ck(r->ctx, nk_fill(r->ctx, acc(&unused), r->dtype, size_t(r->n()), v));
     r->is_zero = false;
   }
   void no_grad() {  // gradient.rs:68-71
@@ -204,16 +219,16 @@ struct MatMulBackward : Backward {
     const void* G = gradient->get();
     const int gdt = gradient->dtype;
     if (left_grad) {  // (M,K)
-      void* d = left_grad->get();
-      float beta = left_grad->acc_beta();
+      float beta;
+      void* d = left_grad->acc(&beta);
       if (t)  // dX += G.W      : (M,N).(N,K)   NN
         gemm(ctx, false, false, M, K, N, G, N, right_data->rptr(), K, beta, d, gdt, left_grad->dtype);
       else    // dA += G.B^T    : (M,N).(K,N)^T NT
         gemm(ctx, false, true, M, K, N, G, N, right_data->rptr(), N, beta, d, gdt, left_grad->dtype);
     }
     if (right_grad) {
-      void* d = right_grad->get();
-      float beta = right_grad->acc_beta();
+      float beta;
+      void* d = right_grad->acc(&beta);
       if (t)  // dW += G^T.X    : (M,N)^T.(M,K) -> (N,K)  TN
         gemm(ctx, true, false, N, K, M, G, N, left_data->rptr(), K, beta, d, gdt, right_grad->dtype);
       else    // dB += A^T.G    : (M,K)^T.(M,N) -> (K,N)  TN
@@ -246,8 +261,8 @@ struct AdditionBackward : Backward {  // addition/mod.rs:52-135 (Left, Right and
   const char* name() const override { return "AdditionBackward"; }
   void acc(GradientP& dst, bool aliased) {
     if (!dst || aliased) return;
-    void* d = dst->get();
-    float beta = dst->acc_beta();
+    float beta;
+    void* d = dst->acc(&beta);
     ck(ctx, nk_unbroadcast_acc(ctx, d, dst->dtype, (int)dst->shape.size(), dst->shape.data(), gradient->get(),
                                gradient->dtype, (int)gradient->shape.size(), gradient->shape.data(), beta));
   }
@@ -272,8 +287,8 @@ struct ReLUBackward : Backward {  // relu/mod.rs:40-79
   GradientP operand_grad;
   const char* name() const override { return "ReLUBackward"; }
   void backward() override {
-    void* d = operand_grad->get();
-    float beta = operand_grad->acc_beta();
+    float beta;
+    void* d = operand_grad->acc(&beta);
     ck(ctx, nk_relu_bwd(ctx, d, operand_data->rptr(), gradient->get(), size_t(operand_data->n()),
                         operand_data->dtype, beta));
   }
@@ -308,8 +323,8 @@ struct SoftmaxBackward : Backward {  // softmax/mod.rs:55-104, logsoftmax/mod.rs
   void backward() override {
     int64_t o, l, i;
     lanes(data->shape, axis, o, l, i);
-    void* d = operand_grad->get();
-    float beta = operand_grad->acc_beta();
+    float beta;
+    void* d = operand_grad->acc(&beta);
     ck(ctx, (log ? nk_log_softmax_bwd : nk_softmax_bwd)(ctx, d, data->rptr(), gradient->get(), o, l, i, data->dtype,
                                                          beta));
   }
@@ -331,8 +346,8 @@ struct SumMeanBackward : Backward {  // sum/mod.rs:36-66, mean/mod.rs:36-71
   bool mean;
   const char* name() const override { return mean ? "MeanBackward" : "SumBackward"; }
   void backward() override {
-    void* d = operand_grad->get();
-    float beta = operand_grad->acc_beta();
+    float beta;
+    void* d = operand_grad->acc(&beta);
     ck(ctx, nk_sum_bwd(ctx, d, (const float*)gradient->get(), size_t(operand_grad->n()), operand_grad->dtype, mean,
                        beta));
   }
@@ -359,8 +374,8 @@ struct LossBackward : Backward {  // squared_error/mod.rs:60-122, nll/mod.rs:70-
   bool mean, nll;
   const char* name() const override { return nll ? "NegativeLogLikelihoodBackward" : "SquaredErrorBackward"; }
   void backward() override {
-    void* d = input_grad->get();
-    float beta = input_grad->acc_beta();
+    float beta;
+    void* d = input_grad->acc(&beta);
     const float* g = (const float*)gradient->get();
     if (nll)
       ck(ctx, nk_nll_bwd(ctx, d, target->rptr(), g, input->shape[0], input->shape[1], input->dtype, mean, beta));
@@ -388,8 +403,8 @@ struct PadBackward : Backward {  // pad/mod.rs:131-182
   const char* name() const override { return "PadBackward"; }
   void backward() override {
     const Shape& s = operand_grad->shape;
-    void* d = operand_grad->get();
-    float beta = operand_grad->acc_beta();
+    float beta;
+    void* d = operand_grad->acc(&beta);
     ck(ctx, nk_pad2d_bwd(ctx, d, gradient->get(), s[0] * s[1], s[2], s[3], ph, pw, operand_grad->dtype, beta));
   }
 };
@@ -415,14 +430,14 @@ struct ConvolutionBackward : Backward {  // convolution/mod.rs:357-510: input fi
   const char* name() const override { return "ConvolutionBackward"; }
   void backward() override {
     if (input_grad) {
-      void* d = input_grad->get();
-      float beta = input_grad->acc_beta();
+      float beta;
+      void* d = input_grad->acc(&beta);
       ck(ctx, nk_conv2d_bwd_input(ctx, d, gradient->get(), kernel->rptr(), a.n, a.cin, a.h, a.w, a.cout, a.kh, a.kw,
                                   a.sh, a.sw, a.dh, a.dw, a.groups, gradient->dtype, beta));
     }
     if (kernel_grad) {
-      void* d = kernel_grad->get();
-      float beta = kernel_grad->acc_beta();
+      float beta;
+      void* d = kernel_grad->acc(&beta);
       ck(ctx, nk_conv2d_bwd_kernel(ctx, d, kernel_grad->dtype, nullptr, gradient->get(), input->rptr(), a.n, a.cin,
                                    a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups, gradient->dtype,
                                    beta));
@@ -675,7 +690,6 @@ int nkg_backward(nkg_var* v, float seed) {
 int nkg_zero_grad(nkg_var* v) {
   return guard([&] {
     if (!v || !v->diff()) fail(NK_ERR_INVALID_ARG, "nkg_zero_grad: not a differentiable variable");
-    v->grad->get();
     v->grad->zero();
   });
 }

@@ -86,6 +86,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Same, for waiters that are NOT on the critical path of the tensor pipe (producers with stages of slack,
+// epilogues behind a double-buffered accumulator): back off between polls so they do not steal issue slots.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_sleep(bar, parity)) {
+    __nanosleep(48);
+    if ((++spins & 63u) != 0) continue;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    if (now - t0 > (1ll << 32)) {
+      printf("nk_b200: mbarrier watchdog: block %d thread %d bar 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");

@@ -510,3 +510,29 @@ def test_conv2d_tensor_core_backward_kernel(nk, dev, O, shape, cout, k):
     dwb = dev.from_ndarray(w0, nk.BF16)
     ops.conv2d_bwd_kernel(dwb, dev.from_ndarray(g, nk.BF16), dev.from_ndarray(x, nk.BF16), beta=0.0)
     assert np.all(np.abs(dwb.as_ndarray() - want) <= 2e-3 * scale + 2.0 ** -8 * np.abs(want) + 1e-5)
+
+
+@pytest.mark.parametrize("shape,cout", [((2, 3, 20, 24), 64), ((1, 3, 224, 224), 64), ((3, 1, 9, 40), 32),
+                                        ((2, 2, 70, 16), 16), ((2, 3, 130, 256), 64)])
+def test_conv2d_tensor_core_backward_input(nk, dev, O, shape, cout):
+    """dX on the tcgen05 engine (3x3, Cin <= 3): col2im in registers, G read once, dx written once; random
+    (non-uniform) kernels and gradients pin the layout the reference's all-ones tests cannot see; beta = 1
+    accumulates into an existing gradient; images taller than one row block exercise the halo recompute."""
+    from neuronika_b200 import ops
+    rng = np.random.default_rng(13)
+    w = O.bf16_round(rnd(rng, (cout, shape[1], 3, 3), -0.3, 0.3))
+    g = O.bf16_round(rnd(rng, (shape[0], cout, shape[2] - 2, shape[3] - 2)))
+    d0 = O.bf16_round(rnd(rng, shape))
+    want = np.zeros(shape, F32)
+    O.conv_backward_input(want, g, w, (1, 1), (1, 1))
+    want = want.astype(np.float64)
+    scale = float(np.sqrt((want ** 2).mean())) + 1e-9
+    dx = dev.zeros(shape, nk.BF16)
+    ops.conv2d_bwd_input(dx, dev.from_ndarray(g, nk.BF16), dev.from_ndarray(w, nk.BF16), beta=0.0)
+    assert dev.last_conv_kernel == "tcgen05_implicit_gemm_dx"
+    err = np.abs(dx.as_ndarray() - want)
+    assert np.all(err <= 2e-3 * scale + 2.0 ** -8 * np.abs(want)), float(err.max())
+    dx1 = dev.from_ndarray(d0, nk.BF16)
+    ops.conv2d_bwd_input(dx1, dev.from_ndarray(g, nk.BF16), dev.from_ndarray(w, nk.BF16), beta=1.0)
+    want1 = want + d0
+    assert np.all(np.abs(dx1.as_ndarray() - want1) <= 2e-3 * scale + 2.0 ** -7 * np.abs(want1))
