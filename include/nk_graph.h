@@ -85,6 +85,12 @@ int nkg_convolution(nkg_var* kernel, nkg_var* input, int64_t sh, int64_t sw, int
 /* (N, C, H, W) -> (N, C*H*W): bit-exact view; not in the reference (SURVEY.md 2.2 "missing") */
 int nkg_flatten(nkg_var* a, nkg_var** out);
 
+/* ---- gradient-ready hook (data parallel overlap): `cb(user)` is called from inside nkg_backward(), on the calling
+ * thread, right after the LAST kernel that accumulates into this leaf's gradient in the running backward pass has
+ * been launched -- so the caller can start the all-reduce of that gradient while the rest of backward runs. */
+typedef void (*nkg_grad_hook)(void* user);
+int nkg_set_grad_hook(nkg_var* leaf, nkg_grad_hook cb, void* user);
+
 /* ---- SGD on a leaf (neuronika-optim/src/sgd/mod.rs:191-231) ---- */
 int nkg_sgd_step(nkg_var* param, float* momentum_buf, float* master, float lr, float l2, float momentum,
                  float dampening, int nesterov, float grad_scale);

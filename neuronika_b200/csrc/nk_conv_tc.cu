@@ -341,7 +341,26 @@ conv_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         __nv_bfloat16* dst = p.y + (int64_t(n) * p.cout + ew) * plane + int64_t(prow) * p.wo + q0;
         const uint8_t* rowp = sg + (c * rows + ew) * 128;
         const int64_t dstep = 8 * plane;
-        if (p.vec >= 2) {
+        const bool row8 = p.vec >= 2 && (((int64_t(prow) * p.wo + q0) & 3) == 0) && ((plane & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.y) & 7) == 0) && valid >= 4;
+        if (row8) {
+          // 8-byte aligned rows (every other output row at Wo = 222): lanes 0-15 / 16-31 move 4 pixels each of TWO
+          // rows (ew + 8k, ew + 8(k+1)) per instruction
+          const int l16 = lane & 15, sub = lane >> 4, px = l16 * 4;
+          const uint8_t* src = rowp + sub * 1024 + ((((px >> 3) ^ (ew & 7))) << 4) + (px & 7) * 2;
+          __nv_bfloat16* d4 = dst + sub * dstep + px;
+          const int nrows = (p.cout - ew + 7) >> 3;
+          for (int k = sub; k < nrows; k += 2, src += 2048, d4 += 2 * dstep) {
+            const uint2 v2 = *reinterpret_cast<const uint2*>(src);
+            if (px + 3 < valid) {
+              *reinterpret_cast<uint2*>(d4) = v2;
+            } else if (px < valid) {
+              const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v2);
+              for (int i = 0; i < 4; ++i)
+                if (px + i < valid) d4[i] = e[i];
+            }
+          }
+        } else if (p.vec >= 2) {
           const int px = lane * 2;
           const uint8_t* src = rowp + ((((px >> 3) ^ (ew & 7))) << 4) + (px & 7) * 2;
           __nv_bfloat16* d2 = dst + px;
@@ -486,8 +505,10 @@ int nk_conv2d_fwd_tc(nk_ctx* ctx, void* y, const void* x, const void* w, const v
 // =====================================================================================================
 namespace {
 
-constexpr int kWThreads = 192;  // warp 0: TMA (x windows), warp 1: MMA + TMEM, warps 2..5: cp.async (G) then epilogue
-constexpr int kWProducers = 128;
+constexpr int kWThreads = 448;  // warp 0: TMA (x windows), warp 1: MMA + TMEM, warps 2..5: shift taps + final epilogue,
+                                // warps 6..13: cp.async (G rows)
+constexpr int kWProducers = 256;
+constexpr int kWShiftThreads = 128;
 
 struct ConvWP {
   int n, cin, h, w, cout, kh, kw, ho, wo;
@@ -540,7 +561,7 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     ptx::prefetch_tmap(&tmap_halo);
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(fullx_bar(s), 1);
-      ptx::mbar_init(ready_bar(s), kWProducers + kWProducers / 32);
+      ptx::mbar_init(ready_bar(s), kWProducers + kWShiftThreads / 32);
       ptx::mbar_init(empty_bar(s), 1);
     }
     ptx::mbar_init(done_bar, 1);
@@ -623,12 +644,11 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       ptx::mma_commit(done_bar);
     }
-  } else {
-    // ---- producers: cp.async G rows into the swizzled K-major A slots, then build the taps j >= 1 of the B slots
-    const int t = threadIdx.x - 64;  // 0..127
-    const int piece = t & 31, co0 = t >> 5, wrp = t >> 5;
-    const uint32_t sw0 = (((piece >> 2) ^ (co0 & 7)) << 4) + (piece & 3) * 4;
-    const uint32_t sw1 = (((piece >> 2) ^ ((co0 + 4) & 7)) << 4) + (piece & 3) * 4;
+  } else if (warp_idx >= 6) {
+    // ---- G loaders: cp.async 4-byte pieces of the G rows into the swizzled K-major A slots (8 warps)
+    const int t = threadIdx.x - 6 * 32;  // 0..255
+    const int piece = t & 31, co0 = t >> 5;   // rows co0, co0 + 8, ...  ((co0 + 8k) & 7 == co0 & 7)
+    const uint32_t sw = (((piece >> 2) ^ (co0 & 7)) << 4) + (piece & 3) * 4;
     int stage = 0;
     uint32_t phase = 0;
     const long long plane = (long long)p.ho * p.wo;
@@ -636,7 +656,6 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int n = int(tl / p.tiles_per_img);
       const int g0 = int(tl - (long long)n * p.tiles_per_img) * kChunksPerTile;
       ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
-      uint8_t* sp = base_ptr + stage * stage_bytes;
       const uint32_t sa = base + stage * stage_bytes;
       int prow = g0 / p.cpr, qc = g0 - prow * p.cpr;
       for (int c = 0; c < kChunksPerTile; ++c, ++qc) {
@@ -651,20 +670,31 @@ conv_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         nbytes = nbytes < 0 ? 0 : (nbytes > 4 ? 4 : nbytes);
         const __nv_bfloat16* src = p.g + (long long)n * p.cout * plane + (long long)co0 * plane +
                                    (nbytes ? (long long)prow * p.wo + q0 + piece * 2 : 0);
-        uint32_t drow = sa + c * chunk_bytes + co0 * 128;
-        for (int co = co0, it = 0; co < p.cout; co += 4, ++it, src += 4 * plane, drow += 512) {
-          const uint32_t dst = drow + ((it & 1) ? sw1 : sw0);
+        uint32_t dst = sa + c * chunk_bytes + co0 * 128 + sw;
+        const long long sstep = 8 * plane;
+#pragma unroll 8
+        for (int co = co0; co < p.cout; co += 8, src += sstep, dst += 1024)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-        }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ready_bar(stage)) : "memory");
-      // taps: slot(j*ng + grp)[r][px] = slot(grp)[r][px + j]   (tap-0 window + 8-pixel halo, see shift_taps)
+      if (++stage == S) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else {
+    // ---- shift warps: taps slot(j*ng + grp)[r][px] = slot(grp)[r][px + j] (tap-0 window + 8-pixel halo, see shift_taps)
+    const int wrp = warp_idx - 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long tl = t_begin; tl < t_end; ++tl) {
+      uint8_t* sp = base_ptr + stage * stage_bytes;
       ptx::mbar_wait_relaxed(fullx_bar(stage), phase);
       for (int c = 0; c < kChunksPerTile; ++c) {
         uint8_t* xs = sp + c * chunk_bytes + g_bytes;
         const uint8_t* halo = xs + x_bytes;
         for (int grp = 0; grp < p.ng; ++grp)
-          for (int r = wrp; r < p.R; r += kWProducers / 32) {
+          for (int r = wrp; r < p.R; r += kWShiftThreads / 32) {
             const uint32_t own = *reinterpret_cast<const uint32_t*>(xs + grp * 2048 + sw128_word(r, lane));
             const uint32_t hl = *reinterpret_cast<const uint32_t*>(halo + grp * 256 + r * 16 + (lane & 3) * 4);
             const uint32_t doff = sw128_word(r, lane);
@@ -838,8 +868,9 @@ int nk_conv2d_bwd_kernel_tc(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, c
 // =====================================================================================================
 namespace {
 
-constexpr int kXThreads = 448;  // warp 0: TMEM reader, warp 1: MMA + TMEM alloc, warps 2..5: cp.async (G), warps 6..13: pixels
-constexpr int kXProducers = 128;
+constexpr int kXThreads = 576;  // warp 0: TMEM reader, warp 1: MMA + TMEM alloc, warps 2..9: G loaders (cp.async), warps 10..17: pixels
+constexpr int kXProducers = 256;  // cp.async loader threads
+constexpr int kXPixelWarp0 = 10;
 constexpr int kSRowFloats = 260;  // padded row of the f32 exchange buffer (conflict-free 16-byte writes per lane)
 
 struct ConvXP {
@@ -991,15 +1022,17 @@ __global__ void __launch_bounds__(kXThreads, 1) conv_dx_tc_kernel(const ConvXP p
         if (sbuf == 0) sphase ^= 1u;
       }
     }
-  } else if (warp_idx < 6) {
-    // ===================================================== producers: cp.async the G row (Cout x Wo) into the B tile
-    const int t = threadIdx.x - 64;
-    const int piece = t & 31, o0 = t >> 5;
+  } else if (warp_idx < kXPixelWarp0) {
+    // ===================================================== G loaders: cp.async the (Cout x Wo) row tile into the B tile.
+    // G rows have a 2*Wo-byte pitch (4-byte aligned only): neither TMA nor 16-byte cp.async can move them.  A plain
+    // LDG.32 -> STS.32 loader was tried and is 2x slower (1.24 ms vs 0.59 ms at config 3: it is latency bound), so
+    // the rows go through 4-byte cp.async, spread over 8 warps.
+    const int t = threadIdx.x - 64;              // 0..255
+    const int piece = t & 31, o0 = t >> 5;       // rows o0, o0 + 8, ...
     int stage = 0;
     uint32_t phase = 0;
     const long long plane = (long long)p.ho * p.wo;
-    const uint32_t sw0 = (((piece >> 2) ^ (o0 & 7)) << 4) + (piece & 3) * 4;
-    const uint32_t sw1 = (((piece >> 2) ^ ((o0 + 4) & 7)) << 4) + (piece & 3) * 4;
+    const uint32_t sw = (((piece >> 2) ^ (o0 & 7)) << 4) + (piece & 3) * 4;   // (o0 + 8k) & 7 == o0 & 7
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       int n, u0, u1, p_lo, p_hi;
       unit_rows(unit, n, u0, u1, p_lo, p_hi);
@@ -1012,11 +1045,11 @@ __global__ void __launch_bounds__(kXThreads, 1) conv_dx_tc_kernel(const ConvXP p
           int nbytes = (p.wo - c * kChunk - piece * 2) * 2;
           nbytes = nbytes < 0 ? 0 : (nbytes > 4 ? 4 : nbytes);
           const __nv_bfloat16* src = grow + (long long)o0 * plane + (nbytes ? c * kChunk + piece * 2 : 0);
-          uint32_t drow = sb + c * chunk_bytes + o0 * 128;
-          for (int o = o0, it = 0; o < p.cout; o += 4, ++it, src += 4 * plane, drow += 512) {
-            const uint32_t dst = drow + ((it & 1) ? sw1 : sw0);
+          uint32_t dst = sb + c * chunk_bytes + o0 * 128 + sw;
+          const long long sstep = 8 * plane;
+#pragma unroll 8
+          for (int o = o0; o < p.cout; o += 8, src += sstep, dst += 1024)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-          }
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(stage)) : "memory");
         if (++stage == S) {
@@ -1027,7 +1060,7 @@ __global__ void __launch_bounds__(kXThreads, 1) conv_dx_tc_kernel(const ConvXP p
     }
   } else {
     // ===================================================== pixel warps: col2im in registers, one dx column each
-    const int v = threadIdx.x - 6 * 32;  // 0..255
+    const int v = threadIdx.x - kXPixelWarp0 * 32;  // 0..255
     const bool col_live = v < p.w;
     int sbuf = 0;
     uint32_t sphase = 0;

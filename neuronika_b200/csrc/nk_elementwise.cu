@@ -211,6 +211,50 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(float* __restrict__ sc
   }
 }
 
+// same, 16-byte loads: 32 column groups x 8 row lanes per block, V = 16/sizeof(T) columns per thread
+template <typename T>
+__global__ void __launch_bounds__(kThreads) colsum_vec_kernel(float* __restrict__ scratch, const T* __restrict__ g,
+                                                             int64_t R0, int64_t K, int64_t rows_per_block) {
+  constexpr int V = NkVec<T>::N;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int64_t col = (int64_t(blockIdx.x) * 32 + cx) * V;
+  const int64_t r_begin = int64_t(blockIdx.y) * rows_per_block;
+  int64_t r_end = r_begin + rows_per_block;
+  if (r_end > R0) r_end = R0;
+  float acc[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[i] = 0.f;
+  if (col < K) {
+    int64_t r = r_begin + ry;
+    for (; r + 8 < r_end; r += 16) {  // two independent loads in flight
+      NkVec<T> a, b;
+      a.load(g + r * K + col);
+      b.load(g + (r + 8) * K + col);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += a.get(i) + b.get(i);
+    }
+    for (; r < r_end; r += 8) {
+      NkVec<T> a;
+      a.load(g + r * K + col);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += a.get(i);
+    }
+  }
+  __shared__ float sm[8][32 * V + 1];
+#pragma unroll
+  for (int i = 0; i < V; ++i) sm[ry][cx * V + i] = acc[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * V; c += kThreads) {
+    const int64_t gc = int64_t(blockIdx.x) * 32 * V + c;
+    if (gc < K) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += sm[i][c];
+      atomicAdd(&scratch[gc], t);
+    }
+  }
+}
+
 // general (R0, K, R1) with R1 > 1: one block per (k, r0-chunk); contiguous runs of R1
 template <typename T>
 __global__ void __launch_bounds__(kThreads) chansum_kernel(float* __restrict__ scratch, const T* __restrict__ g,
@@ -625,7 +669,20 @@ int nk_unbroadcast_acc(nk_ctx* ctx, void* dst, int dst_dtype, int dst_ndim, cons
         R1 *= g_shape[k];
     }
     NK_CUDA(ctx, cudaMemsetAsync(scratch, 0, n_dst * sizeof(float), ctx->stream));
-    if (R1 == 1) {
+    const int V = g_dtype == NK_BF16 ? 8 : 4;
+    if (R1 == 1 && K % V == 0 && aligned16(g) && K >= 32 * V) {
+      const int64_t col_blocks = (K + 32 * V - 1) / (32 * V);
+      int64_t want_y = (int64_t(ctx->sm_count) * 8 + col_blocks - 1) / col_blocks;
+      int64_t rows_per_block = (R0 + want_y - 1) / want_y;
+      if (rows_per_block < 64) rows_per_block = 64;
+      const int64_t gy = (R0 + rows_per_block - 1) / rows_per_block;
+      dim3 grid((unsigned)col_blocks, (unsigned)gy);
+      if (g_dtype == NK_BF16)
+        colsum_vec_kernel<__nv_bfloat16><<<grid, kThreads, 0, ctx->stream>>>(scratch, (const __nv_bfloat16*)g, R0, K, rows_per_block);
+      else
+        colsum_vec_kernel<float><<<grid, kThreads, 0, ctx->stream>>>(scratch, (const float*)g, R0, K, rows_per_block);
+      NK_LAUNCHED(ctx, "colsum_vec");
+    } else if (R1 == 1) {
       int64_t col_blocks = (K + 31) / 32;
       int64_t want_y = (int64_t(ctx->sm_count) * 8 + col_blocks - 1) / col_blocks;
       int64_t rows_per_block = (R0 + want_y - 1) / want_y;

@@ -95,6 +95,10 @@ struct Gradient {
   bool is_zero = true;   // content known to be all zeros -> first accumulate may overwrite
   bool stale = false;    // logically zero but the memory has not been cleared yet (lazy zero_grad)
   std::shared_ptr<Gradient> alias;  // fusion: this gradient IS that gradient
+  nkg_grad_hook hook = nullptr;     // data-parallel overlap: called when the last writer of a backward pass is done
+  void* hook_user = nullptr;
+  int last_writer = -1;             // index (in reverse tape order) of the last node writing it in this pass
+  bool hook_fired = false;
   Gradient(nk_ctx* c, Shape s, int dt) : ctx(c), shape(std::move(s)), dtype(dt) {}
   ~Gradient() {
     if (owned && ptr) nk_free(ctx, ptr);
@@ -167,11 +171,23 @@ struct Forward {
   virtual void forward() = 0;
   virtual const char* name() const = 0;
 };
+// set by nkg_backward around each node: position of the running node in the reverse tape
+static thread_local int g_bwd_pos = -1;
+static inline void grad_written(const GradientP& g) {
+  if (!g) return;
+  Gradient* r = g->root();
+  if (r->hook && r->last_writer == g_bwd_pos && !r->hook_fired) {
+    r->hook_fired = true;
+    r->hook(r->hook_user);
+  }
+}
+
 struct Backward {
   GradientP gradient;  // gradient of this node's output
   bool skip = false;
   virtual ~Backward() {}
   virtual void backward() = 0;
+  virtual void targets(std::vector<Gradient*>& out) = 0;  // gradients this node accumulates into
   virtual const char* name() const = 0;
   virtual void no_grad() {
     if (gradient) gradient->no_grad();
@@ -198,11 +214,11 @@ struct MatMul : Forward {
   MatMul(nk_ctx* c, TensorP l, TensorP r, TensorP d, bool tt) : ctx(c), left(l), right(r), data(d), t(tt) {}
   const char* name() const override { return t ? "MatrixMatrixMulT" : "MatrixMatrixMul"; }
   void forward() override { run(nullptr); }
-  void run(Tensor* bias, Tensor* out = nullptr) {
+  void run(Tensor* bias, Tensor* out = nullptr, int relu = 0) {
     Tensor* o = out ? out : data.get();
     const int64_t M = left->shape[0], K = left->shape[1], N = t ? right->shape[0] : right->shape[1];
     gemm(ctx, false, t, M, N, K, left->rptr(), left->shape[1], right->rptr(), right->shape[1], 0.f, o->wptr(),
-         left->dtype, o->dtype, bias ? bias->rptr() : nullptr, bias ? bias->dtype : NK_F32, 0);
+         left->dtype, o->dtype, bias ? bias->rptr() : nullptr, bias ? bias->dtype : NK_F32, relu);
   }
 };
 
@@ -213,19 +229,17 @@ struct MatMulBackward : Backward {
   GradientP left_grad, right_grad;  // either may be null (operand not differentiable)
   bool t;
   const char* name() const override { return t ? "MatrixMatrixMulTBackward" : "MatrixMatrixMulBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (left_grad) out.push_back(left_grad->root());
+    if (right_grad) out.push_back(right_grad->root());
+  }
   void backward() override {
     const int64_t M = left_data->shape[0], K = left_data->shape[1];
     const int64_t N = t ? right_data->shape[0] : right_data->shape[1];
     const void* G = gradient->get();
     const int gdt = gradient->dtype;
-    if (left_grad) {  // (M,K)
-      float beta;
-      void* d = left_grad->acc(&beta);
-      if (t)  // dX += G.W      : (M,N).(N,K)   NN
-        gemm(ctx, false, false, M, K, N, G, N, right_data->rptr(), K, beta, d, gdt, left_grad->dtype);
-      else    // dA += G.B^T    : (M,N).(K,N)^T NT
-        gemm(ctx, false, true, M, K, N, G, N, right_data->rptr(), N, beta, d, gdt, left_grad->dtype);
-    }
+    // the right operand is the parameter in Linear (dW): issue it first so that its all-reduce can overlap the
+    // dX GEMM under data parallel; the two results are independent, so the order is invisible
     if (right_grad) {
       float beta;
       void* d = right_grad->acc(&beta);
@@ -233,19 +247,40 @@ struct MatMulBackward : Backward {
         gemm(ctx, true, false, N, K, M, G, N, left_data->rptr(), K, beta, d, gdt, right_grad->dtype);
       else    // dB += A^T.G    : (M,K)^T.(M,N) -> (K,N)  TN
         gemm(ctx, true, false, K, N, M, left_data->rptr(), K, G, N, beta, d, gdt, right_grad->dtype);
+      grad_written(right_grad);
+    }
+    if (left_grad) {  // (M,K)
+      float beta;
+      void* d = left_grad->acc(&beta);
+      if (t)  // dX += G.W      : (M,N).(N,K)   NN
+        gemm(ctx, false, false, M, K, N, G, N, right_data->rptr(), K, beta, d, gdt, left_grad->dtype);
+      else    // dA += G.B^T    : (M,N).(K,N)^T NT
+        gemm(ctx, false, true, M, K, N, G, N, right_data->rptr(), N, beta, d, gdt, left_grad->dtype);
+      grad_written(left_grad);
     }
   }
 };
 
 // ------------------------------------------------------------------------------- addition
+struct Convolution;
 struct Addition : Forward {  // addition/mod.rs:11-50
   nk_ctx* ctx;
   TensorP left, right, data;
-  std::shared_ptr<MatMul> fused_gemm;  // peephole: data = mm_t(..) + right in one kernel
+  std::shared_ptr<MatMul> fused_gemm;        // peephole: data = mm_t(..) + right in one kernel
+  std::shared_ptr<Convolution> fused_conv;   // peephole: data = convolution(..) + bias(Cout,1,1) in one kernel
+  TensorP fused_relu_out;                    // peephole: the consumer ReLU's output, written by the GEMM epilogue
+  void run_fused_conv();
   const char* name() const override { return "Addition"; }
   void forward() override {
     if (fused_gemm) {
-      fused_gemm->run(right.get(), data.get());
+      if (fused_relu_out)
+        fused_gemm->run(right.get(), fused_relu_out.get(), 1);  // y = relu(x.W^T + b); z itself is never stored
+      else
+        fused_gemm->run(right.get(), data.get());
+      return;
+    }
+    if (fused_conv) {
+      run_fused_conv();
       return;
     }
     ck(ctx, nk_add_bcast_fwd(ctx, data->wptr(), left->rptr(), right->rptr(), data->dtype, (int)data->shape.size(),
@@ -257,7 +292,7 @@ struct Addition : Forward {  // addition/mod.rs:11-50
 struct AdditionBackward : Backward {  // addition/mod.rs:52-135 (Left, Right and the composite)
   nk_ctx* ctx;
   GradientP left_grad, right_grad;
-  bool left_aliased = false, right_aliased = false;
+  bool left_aliased = false, right_aliased = false;  // right_aliased: the bias gradient is produced by the fused conv dW
   const char* name() const override { return "AdditionBackward"; }
   void acc(GradientP& dst, bool aliased) {
     if (!dst || aliased) return;
@@ -265,6 +300,11 @@ struct AdditionBackward : Backward {  // addition/mod.rs:52-135 (Left, Right and
     void* d = dst->acc(&beta);
     ck(ctx, nk_unbroadcast_acc(ctx, d, dst->dtype, (int)dst->shape.size(), dst->shape.data(), gradient->get(),
                                gradient->dtype, (int)gradient->shape.size(), gradient->shape.data(), beta));
+    grad_written(dst);
+  }
+  void targets(std::vector<Gradient*>& out) override {
+    if (left_grad) out.push_back(left_grad->root());
+    if (right_grad) out.push_back(right_grad->root());
   }
   void backward() override {
     acc(left_grad, left_aliased);
@@ -286,6 +326,9 @@ struct ReLUBackward : Backward {  // relu/mod.rs:40-79
   TensorP operand_data;
   GradientP operand_grad;
   const char* name() const override { return "ReLUBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (operand_grad) out.push_back(operand_grad->root());
+  }
   void backward() override {
     float beta;
     void* d = operand_grad->acc(&beta);
@@ -320,6 +363,9 @@ struct SoftmaxBackward : Backward {  // softmax/mod.rs:55-104, logsoftmax/mod.rs
   int axis;
   bool log;
   const char* name() const override { return log ? "LogSoftmaxBackward" : "SoftmaxBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (operand_grad) out.push_back(operand_grad->root());
+  }
   void backward() override {
     int64_t o, l, i;
     lanes(data->shape, axis, o, l, i);
@@ -345,6 +391,9 @@ struct SumMeanBackward : Backward {  // sum/mod.rs:36-66, mean/mod.rs:36-71
   GradientP operand_grad;
   bool mean;
   const char* name() const override { return mean ? "MeanBackward" : "SumBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (operand_grad) out.push_back(operand_grad->root());
+  }
   void backward() override {
     float beta;
     void* d = operand_grad->acc(&beta);
@@ -373,6 +422,9 @@ struct LossBackward : Backward {  // squared_error/mod.rs:60-122, nll/mod.rs:70-
   GradientP input_grad;
   bool mean, nll;
   const char* name() const override { return nll ? "NegativeLogLikelihoodBackward" : "SquaredErrorBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (input_grad) out.push_back(input_grad->root());
+  }
   void backward() override {
     float beta;
     void* d = input_grad->acc(&beta);
@@ -401,6 +453,9 @@ struct PadBackward : Backward {  // pad/mod.rs:131-182
   GradientP operand_grad;
   int64_t ph, pw;
   const char* name() const override { return "PadBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (operand_grad) out.push_back(operand_grad->root());
+  }
   void backward() override {
     const Shape& s = operand_grad->shape;
     float beta;
@@ -417,17 +472,26 @@ struct Convolution : Forward {  // convolution/mod.rs:296-355
   TensorP input, kernel, data;
   ConvArgs a;
   const char* name() const override { return "Convolution"; }
-  void forward() override {
-    ck(ctx, nk_conv2d_fwd(ctx, data->wptr(), input->rptr(), kernel->rptr(), nullptr, 0, a.n, a.cin, a.h, a.w, a.cout,
-                          a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups, data->dtype));
+  void forward() override { run(nullptr, nullptr); }
+  void run(Tensor* bias, Tensor* out) {
+    Tensor* o = out ? out : data.get();
+    ck(ctx, nk_conv2d_fwd(ctx, o->wptr(), input->rptr(), kernel->rptr(), bias ? bias->rptr() : nullptr, 0, a.n, a.cin,
+                          a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups, o->dtype));
   }
 };
+void Addition::run_fused_conv() { fused_conv->run(right.get(), data.get()); }
 struct ConvolutionBackward : Backward {  // convolution/mod.rs:357-510: input first, then kernel (:380-388)
   nk_ctx* ctx;
   TensorP input, kernel;
   GradientP input_grad, kernel_grad;
+  GradientP bias_grad;  // set by the peephole when the (Cout,1,1) bias add was fused: db rides along with dW
   ConvArgs a;
   const char* name() const override { return "ConvolutionBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (input_grad) out.push_back(input_grad->root());
+    if (kernel_grad) out.push_back(kernel_grad->root());
+    if (bias_grad) out.push_back(bias_grad->root());
+  }
   void backward() override {
     if (input_grad) {
       float beta;
@@ -435,13 +499,29 @@ struct ConvolutionBackward : Backward {  // convolution/mod.rs:357-510: input fi
       ck(ctx, nk_conv2d_bwd_input(ctx, d, gradient->get(), kernel->rptr(), a.n, a.cin, a.h, a.w, a.cout, a.kh, a.kw,
                                   a.sh, a.sw, a.dh, a.dw, a.groups, gradient->dtype, beta));
     }
+    void* dbias = nullptr;
+    if (bias_grad) {
+      float bbeta;
+      void* db = bias_grad->acc(&bbeta);
+      Gradient* kr = kernel_grad ? kernel_grad->root() : nullptr;
+      const float kbeta = kr ? (kr->is_zero ? 0.f : 1.f) : -1.f;
+      if (kr && kbeta == bbeta && bias_grad->dtype == kernel_grad->dtype) {
+        dbias = db;  // same accumulate mode and type as dW: one kernel produces both
+      } else {
+        const int64_t dshape[3] = {a.cout, 1, 1};
+        ck(ctx, nk_unbroadcast_acc(ctx, db, bias_grad->dtype, 3, dshape, gradient->get(), gradient->dtype, 4,
+                                   gradient->shape.data(), bbeta));
+      }
+    }
     if (kernel_grad) {
       float beta;
       void* d = kernel_grad->acc(&beta);
-      ck(ctx, nk_conv2d_bwd_kernel(ctx, d, kernel_grad->dtype, nullptr, gradient->get(), input->rptr(), a.n, a.cin,
+      ck(ctx, nk_conv2d_bwd_kernel(ctx, d, kernel_grad->dtype, dbias, gradient->get(), input->rptr(), a.n, a.cin,
                                    a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups, gradient->dtype,
                                    beta));
+      grad_written(kernel_grad);
     }
+    if (bias_grad) grad_written(bias_grad);
   }
 };
 
@@ -529,6 +609,49 @@ void fuse(nkg_var* v) {
     add->fused_gemm = mm;
     mm->skip = true;
   }
+  // ... followed by ReLU: relu(mm_t + bias) in the same epilogue.  The pre-activation z is then never stored, so the
+  // ReLU backward node masks with y > 0 instead of z > 0 (identical: y = max(z, 0)).
+  {
+    std::map<Tensor*, std::shared_ptr<Addition>> fused_adds;
+    for (auto& kv : v->fwd)
+      if (auto add = std::dynamic_pointer_cast<Addition>(kv.second))
+        if (add->fused_gemm && !add->fused_relu_out) fused_adds[add->data.get()] = add;
+    for (auto& kv : v->fwd) {
+      auto relu = std::dynamic_pointer_cast<ReLU>(kv.second);
+      if (!relu || relu->skip) continue;
+      auto it = fused_adds.find(relu->operand.get());
+      if (it == fused_adds.end()) continue;
+      auto add = it->second;
+      std::shared_ptr<ReLUBackward> rb;
+      for (auto& kb : v->bwd)
+        if (auto c = std::dynamic_pointer_cast<ReLUBackward>(kb.second))
+          if (c->operand_data.get() == add->data.get()) rb = c;
+      // holders of z: the Addition, the ReLU, (the ReLU backward) -- anything else (a live handle, another consumer)
+      // needs z in memory
+      if (add->data.use_count() != (rb ? 3 : 2)) continue;
+      if (relu->data->dtype != add->data->dtype) continue;
+      add->fused_relu_out = relu->data;
+      relu->skip = true;
+      if (rb) rb->operand_data = relu->data;
+    }
+  }
+  // convolution + (Cout,1,1) bias add -> one kernel with a bias epilogue (the Conv2d layer's intended forward)
+  std::map<Tensor*, std::shared_ptr<Convolution>> conv_producers;
+  for (auto& kv : v->fwd)
+    if (auto cv = std::dynamic_pointer_cast<Convolution>(kv.second)) conv_producers[cv->data.get()] = cv;
+  for (auto& kv : v->fwd) {
+    auto add = std::dynamic_pointer_cast<Addition>(kv.second);
+    if (!add || add->fused_gemm || add->fused_conv) continue;
+    auto it = conv_producers.find(add->left.get());
+    if (it == conv_producers.end()) continue;
+    const Shape& os = add->data->shape;
+    const Shape& bs = add->right->shape;
+    if (os.size() != 4 || bs.size() != 3 || bs[0] != os[1] || bs[1] != 1 || bs[2] != 1) continue;
+    if (add->right->dtype != add->data->dtype || add->left->shape != os) continue;
+    if (add->left.use_count() != 2) continue;
+    add->fused_conv = it->second;
+    it->second->skip = true;
+  }
   // gradient aliasing: dL += G with identical shape/dtype and a single consumer => L.grad is G
   for (auto& kv : v->bwd) {
     auto ab = std::dynamic_pointer_cast<AdditionBackward>(kv.second);
@@ -542,6 +665,21 @@ void fuse(nkg_var* v) {
       flag = true;
     };
     try_alias(ab->left_grad, ab->left_aliased);
+  }
+  // bias gradient of a fused Conv2d: let the dW kernel produce it (its all-ones K-row) instead of re-reading G
+  for (auto& kv : v->bwd) {
+    auto ab = std::dynamic_pointer_cast<AdditionBackward>(kv.second);
+    if (!ab || !ab->left_aliased || ab->right_aliased || !ab->right_grad) continue;
+    const Shape& bs = ab->right_grad->shape;
+    if (ab->gradient->shape.size() != 4 || bs.size() != 3 || bs[0] != ab->gradient->shape[1] || bs[1] != 1 || bs[2] != 1)
+      continue;
+    for (auto& kv2 : v->bwd) {
+      auto cb = std::dynamic_pointer_cast<ConvolutionBackward>(kv2.second);
+      if (!cb || cb->bias_grad || cb->gradient->root() != ab->gradient->root()) continue;
+      cb->bias_grad = ab->right_grad;
+      ab->right_aliased = true;
+      break;
+    }
   }
 }
 
@@ -682,8 +820,35 @@ int nkg_backward(nkg_var* v, float seed) {
     if (v->fwd_buf.size() != v->fwd.size() || v->bwd_buf.size() != v->bwd.size())
       fail(NK_ERR_INVALID_ARG, "Perhaps you forgot to call .forward()?");  // vardiff.rs:126-130
     v->grad->fill(seed);
-    for (auto it = v->bwd_buf.rbegin(); it != v->bwd_buf.rend(); ++it)
+    // last writer (reverse tape position) of every hooked gradient in this pass
+    std::vector<Gradient*> tg;
+    bool any_hook = false;
+    int pos = 0;
+    for (auto it = v->bwd_buf.rbegin(); it != v->bwd_buf.rend(); ++it, ++pos) {
+      tg.clear();
+      (*it)->targets(tg);
+      for (Gradient* g : tg)
+        if (g->hook) {
+          g->last_writer = pos;
+          g->hook_fired = false;
+          any_hook = true;
+        }
+    }
+    pos = 0;
+    for (auto it = v->bwd_buf.rbegin(); it != v->bwd_buf.rend(); ++it, ++pos) {
+      g_bwd_pos = any_hook ? pos : -2;
       if (!(*it)->skip) (*it)->backward();
+      if (any_hook) {  // nodes that do not report their writes individually: fire at node granularity
+        tg.clear();
+        (*it)->targets(tg);
+        for (Gradient* g : tg)
+          if (g->hook && g->last_writer == pos && !g->hook_fired) {
+            g->hook_fired = true;
+            g->hook(g->hook_user);
+          }
+      }
+    }
+    g_bwd_pos = -1;
   });
 }
 
@@ -985,6 +1150,15 @@ int nkg_flatten(nkg_var* a, nkg_var** out) {
     v->fwd_buf.clear();
     v->bwd_buf.clear();
     *out = v;
+  });
+}
+
+int nkg_set_grad_hook(nkg_var* leaf, nkg_grad_hook cb, void* user) {
+  return guard([&] {
+    if (!leaf || !leaf->diff()) fail(NK_ERR_INVALID_ARG, "nkg_set_grad_hook: not a differentiable variable");
+    Gradient* r = leaf->grad->root();
+    r->hook = cb;
+    r->hook_user = user;
   });
 }
 

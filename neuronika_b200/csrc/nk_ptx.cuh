@@ -90,10 +90,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // epilogues behind a double-buffered accumulator): back off between polls so they do not steal issue slots.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
+  uint32_t spins = 0, ns = 32;
   long long t0 = 0;
   while (!mbar_try_wait_sleep(bar, parity)) {
-    __nanosleep(48);
+    __nanosleep(ns);
+    if (ns < 512) ns <<= 1;  // exponential back-off: these waiters have slack, the issue slots are worth more
     if ((++spins & 63u) != 0) continue;
     const long long now = clock64();
     if (t0 == 0) t0 = now;

@@ -73,3 +73,46 @@ class GradientBucket:
                 dist.all_reduce(t)
         else:
             dist.all_reduce(t)
+
+
+class OverlappedAllReduce:
+    """All-reduce groups of leaf gradients (contiguous slices of a GradientBucket) on a side stream as soon as
+    backward has produced them, so the exchange overlaps the remaining backward kernels.
+
+        sync = OverlappedAllReduce(bucket, compute_stream, groups=[[0, 1], [2, 3], [4, 5]], params=params)
+        loss.backward(1.0)        # hooks fire inside; every group's all-reduce is in flight when this returns
+        sync.wait()               # compute stream waits for the exchanges; then optimizer.step()
+    """
+
+    def __init__(self, bucket: GradientBucket, compute_stream, groups, params):
+        import torch
+        self.torch = torch
+        self.bucket, self.compute, self.params = bucket, compute_stream, params
+        self.comm = torch.cuda.Stream(device=bucket.array.device.index)
+        self.event = torch.cuda.Event()
+        flat = bucket.as_torch()
+        self.groups = []
+        lay = bucket.layout
+        for g in groups:
+            lo = lay.offsets[g[0]]
+            last = g[-1]
+            hi = lay.offsets[last] + (int(np.prod(lay.shapes[last])) if lay.shapes[last] else 1)
+            self.groups.append({"members": list(g), "view": flat[lo:hi], "pending": len(g)})
+        for gi, g in enumerate(self.groups):
+            for pi in g["members"]:
+                params[pi].set_grad_hook(lambda gi=gi: self._ready(gi))
+
+    def _ready(self, gi: int) -> None:
+        import torch.distributed as dist
+        g = self.groups[gi]
+        g["pending"] -= 1
+        if g["pending"] > 0:
+            return
+        g["pending"] = len(g["members"])
+        self.event.record(self.compute)          # everything launched so far (incl. the kernels that wrote the grads)
+        self.comm.wait_event(self.event)
+        with self.torch.cuda.stream(self.comm):
+            dist.all_reduce(g["view"])
+
+    def wait(self) -> None:
+        self.compute.wait_stream(self.comm)

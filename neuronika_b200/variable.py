@@ -54,11 +54,15 @@ _G = {
     "nkg_convolution": (i32, [vp, vp, i64, i64, i64, i64, i64, pvp]),
     "nkg_flatten": (i32, [vp, pvp]),
     "nkg_sgd_step": (i32, [vp, vp, vp, f32, f32, f32, f32, i32, f32]),
+    "nkg_set_grad_hook": (i32, [vp, vp, vp]),
 }
 for _n, (_r, _a) in _G.items():
     _f = getattr(lib, _n)
     _f.restype = _r
     _f.argtypes = _a
+
+
+GRAD_HOOK = C.CFUNCTYPE(None, vp)
 
 
 def graph_symbols():
@@ -229,6 +233,17 @@ class VarDiff(Var):
 
     def backward_history_len(self) -> int:
         return int(lib.nkg_backward_history_len(self._h))
+
+    def set_grad_hook(self, fn) -> None:
+        """Call `fn()` from inside backward() as soon as this leaf's gradient is final for the running pass
+        (used to overlap the data-parallel all-reduce with the rest of backward)."""
+        if fn is None:
+            self._hook_ref = None
+            _ck(lib.nkg_set_grad_hook(self._h, None, None))
+            return
+        cb = GRAD_HOOK(lambda _user: fn())
+        self._hook_ref = cb  # keep the trampoline alive
+        _ck(lib.nkg_set_grad_hook(self._h, C.cast(cb, vp), None))
 
 
 # ---- constructors (neuronika-variable/src/lib.rs:51-240), on a device
