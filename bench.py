@@ -272,8 +272,7 @@ def run_own(args):
     # produced it (gradient-ready hooks), overlapping the exchange with the remaining backward kernels
     sync = None
     if world > 1:
-        groups = [[i, i + 1] for i in range(0, len(params), 2)]
-        sync = OverlappedAllReduce(bucket, stream, groups, params)
+        sync = OverlappedAllReduce(bucket, stream, params)
 
     def exchange_and_update():
         if sync is not None:

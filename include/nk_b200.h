@@ -158,6 +158,14 @@ int nk_conv2d_bwd_kernel(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, cons
                          const void* x, int64_t n, int64_t cin, int64_t h, int64_t wd,
                          int64_t cout, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t dh,
                          int64_t dw, int64_t groups, int dtype, float beta);
+/* Both halves of ConvolutionBackward::backward (convolution/mod.rs:146-226, which runs the input and
+ * the kernel half back to back) in one call: dx = beta_dx*dx + ..., dw = beta_dw*dw + ...,
+ * dbias likewise (or NULL).  Where the tensor-core path applies the output gradient is streamed
+ * ONCE for both; otherwise it is the two calls above in sequence.  Same results either way. */
+int nk_conv2d_bwd(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int dw_dtype, void* dbias,
+                  float beta_dw, const void* g, const void* x, const void* w, int64_t n,
+                  int64_t cin, int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw,
+                  int64_t sh, int64_t sw, int64_t dh, int64_t dw, int64_t groups, int dtype);
 /* name of the kernel variant the last conv call used */
 const char* nk_last_conv_kernel(nk_ctx* ctx);
 

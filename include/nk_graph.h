@@ -85,11 +85,14 @@ int nkg_convolution(nkg_var* kernel, nkg_var* input, int64_t sh, int64_t sw, int
 /* (N, C, H, W) -> (N, C*H*W): bit-exact view; not in the reference (SURVEY.md 2.2 "missing") */
 int nkg_flatten(nkg_var* a, nkg_var** out);
 
-/* ---- gradient-ready hook (data parallel overlap): `cb(user)` is called from inside nkg_backward(), on the calling
- * thread, right after the LAST kernel that accumulates into this leaf's gradient in the running backward pass has
- * been launched -- so the caller can start the all-reduce of that gradient while the rest of backward runs. */
-typedef void (*nkg_grad_hook)(void* user);
-int nkg_set_grad_hook(nkg_var* leaf, nkg_grad_hook cb, void* user);
+/* ---- gradient-ready hook (data parallel overlap): `cb(user, begin, end)` is called from inside nkg_backward(), on
+ * the calling thread, right after the LAST kernel that accumulates into elements [begin, end) of this leaf's gradient
+ * in the running backward pass has been launched -- so the caller can start the all-reduce of that range while the
+ * rest of backward runs.  Normally one call with [0, numel).  With row_chunks > 1, a matmul backward node that is the
+ * last writer of the gradient computes it in that many row blocks (one GEMM each, same arithmetic per element) and
+ * reports every block as soon as it is launched, so a single large layer's exchange overlaps its own dW GEMMs. */
+typedef void (*nkg_grad_hook)(void* user, int64_t elem_begin, int64_t elem_end);
+int nkg_set_grad_hook(nkg_var* leaf, nkg_grad_hook cb, void* user, int row_chunks);
 
 /* ---- SGD on a leaf (neuronika-optim/src/sgd/mod.rs:191-231) ---- */
 int nkg_sgd_step(nkg_var* param, float* momentum_buf, float* master, float lr, float l2, float momentum,

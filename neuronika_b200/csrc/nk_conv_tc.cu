@@ -1171,3 +1171,482 @@ int nk_conv2d_bwd_input_tc(nk_ctx* ctx, void* dx, const void* g, const void* w, 
   ctx->last_conv_kernel = "tcgen05_implicit_gemm_dx";
   return NK_OK;
 }
+
+
+// =====================================================================================================
+// Fused ConvolutionBackward: dW (+ dbias) and dX in ONE pass over the output gradient
+//   (convolution/mod.rs:146-226: the reference's backward() runs both halves back to back, each streaming G)
+//
+// The dW kernel wants the G row tile as the K-major A operand [Cout rows][64 px] x 4 chunks; the dX kernel wants the
+// very same bytes as the MN-major B operand [k = Cout][256 px] (64-px swizzle atoms, leading byte offset = the chunk
+// stride).  So one cp.async pass feeds both UMMA chains:
+//   dX:  D0[(c,i,j)][px]  = sum_o Wt[(c,i,j)][o] * G[o][px]      (TMEM columns [0,256), drained every row)
+//   dW:  Da[co][k]       += sum_px G[co][px] * Xwin[k][px]       (TMEM columns 256.., `nacc` round-robin accumulators,
+//                                                                 kept for all rows the CTA owns)
+// A CTA owns blocks of dx rows of one image; the kh-1 halo rows of G it recomputes for dX are NOT added to dW (and
+// their x windows are not fetched).  G is read ~1.04x, x ~1x, dx written once.
+// =====================================================================================================
+namespace {
+
+constexpr int kFThreads = 768;  // warp 0: TMEM reader (dX), 1: MMA + TMEM alloc, 2: TMA (x windows), 3: idle,
+                                // 4..7: shift taps + dW epilogue, 8..15: cp.async G loaders, 16..23: dX pixel warps
+constexpr int kFShiftWarp0 = 4, kFLoadWarp0 = 8, kFPixelWarp0 = 16;
+
+struct ConvBP {
+  int n, cin, h, w, cout, ho, wo;
+  int rb, blocks_per_img, num_units, stages, kblocks;
+  int cpr, cpg, ng, ksteps, ncols, R, nacc, fuse_dbias;
+  const __nv_bfloat16* g;
+  const __nv_bfloat16* wt;
+  __nv_bfloat16* dx;
+  float beta_dx;
+  float* scratch;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(kFThreads, 1)
+conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_halo,
+                      const ConvBP p) {
+  constexpr int KH = 3, KW = 3, M = CIN * KH * KW;
+  static_assert(M <= 32, "the (c,i,j) rows must fit one TMEM lane quarter");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_u32);
+  // layout: [dX weights kblocks x 4 KB (32 rows; the M = 128 UMMA over-reads into stage memory, lanes >= 32 unused)]
+  //         [stages x 4 chunks x (G slot Cout x 128 B | X slots ksteps x 2 KB | halo 1 KB)][S: M rows x 1040 B][barriers]
+  const uint32_t g_bytes = p.cout * 128;
+  const uint32_t x_bytes = p.ksteps * 2048;
+  const uint32_t chunk_bytes = g_bytes + x_bytes + 1024;
+  const uint32_t stage_bytes = kChunksPerTile * chunk_bytes;
+  const uint32_t st_off = p.kblocks * 4096;
+  const uint32_t s_off = st_off + p.stages * stage_bytes;
+  const uint32_t s_bytes = M * kSRowFloats * 4;
+  const uint32_t bar_off = s_off + ((s_bytes + 15u) & ~15u);
+  const uint32_t bar_base = base + bar_off;
+  const int S = p.stages;
+  auto fullx_bar = [&](int s) { return bar_base + 8u * s; };
+  auto ready_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  const uint32_t d_full_bar = bar_base + 8u * (3 * S), d_empty_bar = d_full_bar + 8, s_full_bar = d_full_bar + 16,
+                 s_empty_bar = d_full_bar + 24, done_bar = d_full_bar + 32, tmem_slot = d_full_bar + 40;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (3 * S) + 40);
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  {
+    uint4* z = reinterpret_cast<uint4*>(base_ptr);
+    for (uint32_t i = threadIdx.x; i < s_off / 16; i += kFThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  // dX A operand: A[m][o] = W[o][c][i][j], m = (c*KH + i)*KW + j ; K-major SWIZZLE_128B, 64 output channels per block
+  for (int idx = threadIdx.x; idx < p.cout * M; idx += kFThreads) {
+    const int o = idx / M, m = idx - o * M;
+    const int blk = o >> 6, col = o & 63;
+    const uint32_t off = blk * 4096 + m * 128 + (((col >> 3) ^ (m & 7)) << 4) + (col & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(base_ptr + off) = p.wt[idx];
+  }
+  if (p.fuse_dbias) {  // ones row: X slot 0, row 15 of every chunk (no box and no shift writes rows >= R, R <= 15)
+    for (int i = threadIdx.x; i < S * kChunksPerTile * 32; i += kFThreads) {
+      const int sc = i / 32, wq = i % 32;
+      const int s = sc / kChunksPerTile, c = sc % kChunksPerTile;
+      *reinterpret_cast<uint32_t*>(base_ptr + st_off + s * stage_bytes + c * chunk_bytes + g_bytes + 15 * 128 + wq * 4) =
+          0x3F803F80u;
+    }
+  }
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_x);
+    ptx::prefetch_tmap(&tmap_halo);
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(fullx_bar(s), 1);
+      ptx::mbar_init(ready_bar(s), 256 + 4);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    ptx::mbar_init(d_full_bar, 1);
+    ptx::mbar_init(d_empty_bar, 1);
+    ptx::mbar_init(s_full_bar, 1);
+    ptx::mbar_init(s_empty_bar, 8);
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_dw = tmem_base + 256u;
+
+  // every role walks the same sequence of (unit, G row) tiles; G row pr feeds dW only when the unit owns it (pr >= u0)
+  auto unit_rows = [&](int unit, int& n, int& u0, int& u1, int& p_lo, int& p_hi) {
+    n = unit / p.blocks_per_img;
+    const int b = unit - n * p.blocks_per_img;
+    u0 = b * p.rb;
+    u1 = min(u0 + p.rb, p.h);
+    p_lo = max(0, u0 - (KH - 1));
+    p_hi = min(p.ho, u1) - 1;
+  };
+  bool any_owned = false;
+
+  if (warp_idx == 1) {
+    if (lane == 0) {  // ===================================================== MMA issuer
+      const uint32_t idesc_dx = ptx::make_idesc_bf16(128, 256, false, true);
+      const uint32_t idesc_dw = ptx::make_idesc_bf16(128, p.ncols, false, false);
+      int stage = 0;
+      uint32_t phase = 0, dphase = 0, started = 0, cnt = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        int n, u0, u1, p_lo, p_hi;
+        unit_rows(unit, n, u0, u1, p_lo, p_hi);
+        for (int pr = p_lo; pr <= p_hi; ++pr) {
+          ptx::mbar_wait(ready_bar(stage), phase);
+          ptx::fence_proxy_async();  // cp.async / st.shared (generic proxy) writes -> async proxy (UMMA)
+          ptx::mbar_wait(d_empty_bar, dphase ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t sb = base + st_off + stage * stage_bytes;
+          for (int ks = 0; ks < p.cout / 16; ++ks) {
+            const uint64_t adesc = ptx::make_smem_desc_sw128(base + (ks >> 2) * 4096 + (ks & 3) * 32, 16, 1024);
+            const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + ks * 2048, chunk_bytes, 1024);
+            ptx::mma_f16_ss(tmem_base, adesc, bdesc, idesc_dx, ks != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(d_full_bar);
+          dphase ^= 1u;
+          if (pr >= u0) {
+            for (int c = 0; c < p.cpr; ++c) {
+              const uint64_t adesc = ptx::make_smem_desc_sw128(sb + c * chunk_bytes, 16, 1024);
+              const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + c * chunk_bytes + g_bytes, 16, 1024);
+#pragma unroll
+              for (int kq = 0; kq < 4; ++kq) {
+                const uint32_t a = (cnt++) & uint32_t(p.nacc - 1);
+                ptx::mma_f16_ss(tmem_dw + a * uint32_t(p.ncols), adesc + uint64_t(kq * 2), bdesc + uint64_t(kq * 2),
+                                idesc_dw, (started >> a) & 1u);
+                started |= 1u << a;
+              }
+            }
+          }
+          ptx::mma_commit(empty_bar(stage));
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+      ptx::mma_commit(done_bar);
+    }
+  } else if (warp_idx == 0) {
+    // ===================================================== TMEM reader: dX rows (c,i,j) -> f32 exchange buffer
+    uint32_t rphase = 0, sphase = 0;
+    float* srow = reinterpret_cast<float*>(base_ptr + s_off) + (lane < M ? lane : 0) * kSRowFloats;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int n, u0, u1, p_lo, p_hi;
+      unit_rows(unit, n, u0, u1, p_lo, p_hi);
+      for (int pr = p_lo; pr <= p_hi; ++pr) {
+        ptx::mbar_wait(d_full_bar, rphase);
+        ptx::tc_fence_after();
+        ptx::mbar_wait(s_empty_bar, sphase ^ 1u);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + uint32_t(c0), r);
+          ptx::tmem_ld_wait();
+          if (lane < M) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+              *reinterpret_cast<uint4*>(srow + c0 + v * 4) = make_uint4(r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(d_empty_bar);
+          ptx::mbar_arrive(s_full_bar);
+        }
+        rphase ^= 1u;
+        sphase ^= 1u;
+      }
+    }
+  } else if (warp_idx == 2) {
+    if (lane == 0) {  // ===================================================== TMA: tap-0 x windows + halos of owned rows
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = uint32_t(p.cpr) * p.ng * (64u + 8u) * 2u * p.R;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        int n, u0, u1, p_lo, p_hi;
+        unit_rows(unit, n, u0, u1, p_lo, p_hi);
+        for (int pr = p_lo; pr <= p_hi; ++pr) {
+          ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
+          if (pr >= u0) {
+            ptx::mbar_expect_tx(fullx_bar(stage), tx);
+            for (int c = 0; c < p.cpr; ++c) {
+              const uint32_t sc = base + st_off + stage * stage_bytes + c * chunk_bytes + g_bytes;
+              for (int grp = 0; grp < p.ng; ++grp) {
+                ptx::tma_load_4d(sc + grp * 2048, &tmap_x, fullx_bar(stage), c * kChunk, pr, grp * p.cpg, n);
+                ptx::tma_load_4d(sc + x_bytes + grp * 256, &tmap_halo, fullx_bar(stage), (c + 1) * kChunk, pr,
+                                 grp * p.cpg, n);
+              }
+            }
+          } else {
+            ptx::mbar_arrive(fullx_bar(stage));
+          }
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp_idx >= kFShiftWarp0 && warp_idx < kFLoadWarp0) {
+    // ===================================================== shift warps: taps j = 1, 2 of the x windows (two K-rows per
+    // instruction, see shift_taps_kw3), then the dW epilogue
+    const int wrp = warp_idx - kFShiftWarp0;
+    const int l16 = lane & 15, sub = lane >> 4;
+    const int pairs = (p.R + 1) >> 1;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int n, u0, u1, p_lo, p_hi;
+      unit_rows(unit, n, u0, u1, p_lo, p_hi);
+      for (int pr = p_lo; pr <= p_hi; ++pr) {
+        ptx::mbar_wait_relaxed(fullx_bar(stage), phase);
+        if (pr >= u0) {
+          any_owned = true;  // at least one dW chain ran: every accumulator has been written (16 UMMAs >= nacc)
+          uint8_t* sp = base_ptr + st_off + stage * stage_bytes;
+          for (int c = 0; c < p.cpr; ++c) {
+            uint8_t* xs = sp + c * chunk_bytes + g_bytes;
+            const uint8_t* halo = xs + x_bytes;
+            for (int grp = 0; grp < p.ng; ++grp)
+              for (int q = wrp; q < pairs; q += 4) {
+                const int r = q * 2 + sub;
+                const bool live = r < p.R;
+                const int rr = live ? r : 0;
+                const uint32_t off = sw128_word(rr, 2 * l16);
+                const uint2 own = *reinterpret_cast<const uint2*>(xs + grp * 2048 + off);
+                const uint32_t h0 = *reinterpret_cast<const uint32_t*>(halo + grp * 256 + rr * 16);
+                uint32_t n0 = __shfl_down_sync(0xffffffffu, own.x, 1);
+                if (l16 == 15) n0 = h0;
+                if (live) {
+                  uint2 o1;
+                  o1.x = __funnelshift_r(own.x, own.y, 16);
+                  o1.y = __funnelshift_r(own.y, n0, 16);
+                  *reinterpret_cast<uint2*>(xs + (p.ng + grp) * 2048 + off) = o1;
+                  *reinterpret_cast<uint2*>(xs + (2 * p.ng + grp) * 2048 + off) = make_uint2(own.y, n0);
+                }
+              }
+          }
+          ptx::fence_proxy_async();
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ready_bar(stage));
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    // ---- dW epilogue: one pass of atomics per CTA
+    ptx::mbar_wait(done_bar, 0);
+    ptx::tc_fence_after();
+    if (any_owned) {
+      const int q = warp_idx & 3;
+      const int co = q * 32 + lane;
+      if (q * 32 < p.cout) {
+        for (int c0 = 0; c0 < p.ncols; c0 += 16) {
+          float sum[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) sum[jj] = 0.f;
+          for (int a = 0; a < p.nacc; ++a) {
+            uint32_t r[16];
+            ptx::tmem_ld_32x32b_x16(tmem_dw + (uint32_t(q * 32) << 16) + uint32_t(a * p.ncols + c0), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) sum[jj] += __uint_as_float(r[jj]);
+          }
+          if (co < p.cout) {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) atomicAdd(&p.scratch[co * p.ncols + c0 + jj], sum[jj]);
+          }
+        }
+      }
+    }
+  } else if (warp_idx >= kFLoadWarp0 && warp_idx < kFPixelWarp0) {
+    // ===================================================== G loaders: 4-byte cp.async pieces of the (Cout x Wo) row tile
+    const int t = threadIdx.x - kFLoadWarp0 * 32;  // 0..255
+    const int piece = t & 31, o0 = t >> 5;         // rows o0, o0 + 8, ...
+    int stage = 0;
+    uint32_t phase = 0;
+    const long long plane = (long long)p.ho * p.wo;
+    const uint32_t sw = (((piece >> 2) ^ (o0 & 7)) << 4) + (piece & 3) * 4;   // (o0 + 8k) & 7 == o0 & 7
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int n, u0, u1, p_lo, p_hi;
+      unit_rows(unit, n, u0, u1, p_lo, p_hi);
+      for (int pr = p_lo; pr <= p_hi; ++pr) {
+        ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
+        const uint32_t sb = base + st_off + stage * stage_bytes;
+        const __nv_bfloat16* grow = p.g + (long long)n * p.cout * plane + (long long)pr * p.wo;
+#pragma unroll
+        for (int c = 0; c < kChunksPerTile; ++c) {
+          int nbytes = (p.wo - c * kChunk - piece * 2) * 2;
+          nbytes = nbytes < 0 ? 0 : (nbytes > 4 ? 4 : nbytes);
+          const __nv_bfloat16* src = grow + (long long)o0 * plane + (nbytes ? c * kChunk + piece * 2 : 0);
+          uint32_t dst = sb + c * chunk_bytes + o0 * 128 + sw;
+          const long long sstep = 8 * plane;
+#pragma unroll 8
+          for (int o = o0; o < p.cout; o += 8, src += sstep, dst += 1024)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ready_bar(stage)) : "memory");
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp_idx >= kFPixelWarp0) {
+    // ===================================================== pixel warps: col2im in registers, one dx column each
+    const int v = threadIdx.x - kFPixelWarp0 * 32;  // 0..255
+    const bool col_live = v < p.w;
+    uint32_t sphase = 0;
+    const long long img = (long long)p.h * p.w;
+    const float* Sb = reinterpret_cast<const float*>(base_ptr + s_off);
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+      int n, u0, u1, p_lo, p_hi;
+      unit_rows(unit, n, u0, u1, p_lo, p_hi);
+      float ring[CIN][KH];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int k = 0; k < KH; ++k) ring[c][k] = 0.f;
+      __nv_bfloat16* dxn = p.dx + (long long)n * CIN * img + v;
+      auto emit = [&](int u) {  // ring[.][0] holds the finished dx row u of every channel
+        if (u >= u0 && u < u1 && col_live) {
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            __nv_bfloat16* d = dxn + (long long)c * img + (long long)u * p.w;
+            float val = ring[c][0];
+            if (p.beta_dx != 0.f) val += p.beta_dx * __bfloat162float(*d);
+            *d = __float2bfloat16_rn(val);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+#pragma unroll
+          for (int k = 0; k + 1 < KH; ++k) ring[c][k] = ring[c][k + 1];
+          ring[c][KH - 1] = 0.f;
+        }
+      };
+      for (int pr = p_lo; pr <= p_hi; ++pr) {
+        ptx::mbar_wait_relaxed(s_full_bar, sphase);
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+#pragma unroll
+          for (int i = 0; i < KH; ++i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) {
+              const int q = v - j;
+              if (q >= 0) acc += Sb[((c * KH + i) * KW + j) * kSRowFloats + q];
+            }
+            ring[c][i] += acc;
+          }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(s_empty_bar);
+        sphase ^= 1u;
+        emit(pr);
+      }
+      for (int u = p_hi + 1; u < u1; ++u) emit(u);  // rows below the last G row (last block of an image)
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int CIN>
+int launch_bwd_fused(nk_ctx* ctx, const CUtensorMap& tm, const CUtensorMap& tmh, const ConvBP& p, int grid, size_t smem) {
+  auto kern = conv_bwd_fused_kernel<CIN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_done = true;
+  }
+  kern<<<grid, kFThreads, smem, ctx->stream>>>(tm, tmh, p);
+  NK_LAUNCHED(ctx, "conv_bwd_fused_tc");
+  return NK_OK;
+}
+
+}  // namespace
+
+int nk_conv2d_bwd_fused_tc(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int dw_dtype, void* dbias, float beta_dw,
+                           const void* g, const void* x, const void* w, int64_t n, int64_t cin, int64_t h, int64_t wd,
+                           int64_t cout, int64_t kh, int64_t kw) {
+  if (getenv("NK_CONV_DIRECT") || getenv("NK_CONV_UNFUSED_BWD")) return NK_ERR_UNSUPPORTED;
+  if (!ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
+  if (kh != 3 || kw != 3 || cin < 1 || cin > 3) return NK_ERR_UNSUPPORTED;
+  if (cout % 16 != 0 || cout > 128 || wd > 256 || (wd % 8) != 0 || n > 65535) return NK_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(x) & 15) return NK_ERR_UNSUPPORTED;
+  ConvBP p;
+  p.n = (int)n, p.cin = (int)cin, p.h = (int)h, p.w = (int)wd, p.cout = (int)cout;
+  p.ho = int(h - kh + 1), p.wo = int(wd - kw + 1);
+  if ((p.wo & 1) || (reinterpret_cast<uintptr_t>(g) & 3)) return NK_ERR_UNSUPPORTED;  // 4-byte cp.async pieces
+  p.cpg = 16 / 3;
+  if (p.cpg > p.cin) p.cpg = p.cin;
+  p.R = p.cpg * 3;
+  p.ng = (p.cin + p.cpg - 1) / p.cpg;
+  p.ksteps = 3 * p.ng;
+  p.ncols = p.ksteps * 16;
+  p.fuse_dbias = (dbias != nullptr && p.R < 16) ? 1 : 0;
+  p.nacc = 1;
+  while (p.nacc * 2 * p.ncols <= 256 && p.nacc < 16) p.nacc *= 2;
+  p.cpr = (p.wo + kChunk - 1) / kChunk;
+  p.kblocks = (p.cout + 63) / 64;
+  const size_t stage_bytes = size_t(kChunksPerTile) * (p.cout * 128 + p.ksteps * 2048 + 1024);
+  const size_t s_bytes = (size_t(p.cin) * 9 * kSRowFloats * 4 + 15) & ~size_t(15);
+  const size_t fixed = 1024 + size_t(p.kblocks) * 4096 + s_bytes + 512;
+  if (fixed + 2 * stage_bytes > 232448) return NK_ERR_UNSUPPORTED;
+  p.stages = int((232448 - fixed) / stage_bytes);
+  if (p.stages > 4) p.stages = 4;
+  p.rb = 56;
+  if (p.h < 2 * p.rb) p.rb = p.h;
+  p.blocks_per_img = (p.h + p.rb - 1) / p.rb;
+  p.num_units = p.n * p.blocks_per_img;
+  p.g = static_cast<const __nv_bfloat16*>(g);
+  p.wt = static_cast<const __nv_bfloat16*>(w);
+  p.dx = static_cast<__nv_bfloat16*>(dx);
+  p.beta_dx = beta_dx;
+  float* scratch;
+  int rc = nk_workspace(ctx, size_t(128) * p.ncols * sizeof(float), (void**)&scratch);
+  if (rc) return rc;
+  CUtensorMap tm, tmh;
+  if (make_x_tmap(ctx, &tm, x, n, cin, h, wd, 64, 3, p.cpg, true) != NK_OK) return NK_ERR_UNSUPPORTED;
+  if (make_x_tmap(ctx, &tmh, x, n, cin, h, wd, 8, 3, p.cpg, false) != NK_OK) return NK_ERR_UNSUPPORTED;
+  if (dbias && !p.fuse_dbias) {
+    int64_t dshape[3] = {cout, 1, 1};
+    int64_t gshape[4] = {n, cout, p.ho, p.wo};
+    rc = nk_unbroadcast_acc(ctx, dbias, dw_dtype, 3, dshape, g, NK_BF16, 4, gshape, beta_dw);
+    if (rc) return rc;
+    rc = nk_workspace(ctx, size_t(128) * p.ncols * sizeof(float), (void**)&scratch);
+    if (rc) return rc;
+  }
+  p.scratch = scratch;
+  NK_CUDA(ctx, cudaMemsetAsync(scratch, 0, size_t(128) * p.ncols * sizeof(float), ctx->stream));
+  const size_t smem = fixed + size_t(p.stages) * stage_bytes;
+  const int grid = p.num_units < ctx->sm_count ? p.num_units : ctx->sm_count;
+  rc = cin == 1 ? launch_bwd_fused<1>(ctx, tm, tmh, p, grid, smem)
+       : cin == 2 ? launch_bwd_fused<2>(ctx, tm, tmh, p, grid, smem)
+                  : launch_bwd_fused<3>(ctx, tm, tmh, p, grid, smem);
+  if (rc) return rc;
+  const int total = int(cout * cin * 9 + cout);
+  const int blocks = (total + 255) / 256;
+  if (dw_dtype == NK_BF16)
+    conv_dw_finalize<__nv_bfloat16><<<blocks, 256, 0, ctx->stream>>>((__nv_bfloat16*)dwt, (__nv_bfloat16*)dbias, scratch, p.cout, p.cin, 3, 3, p.cpg, p.ng, p.ncols, beta_dw, p.fuse_dbias);
+  else
+    conv_dw_finalize<float><<<blocks, 256, 0, ctx->stream>>>((float*)dwt, (float*)dbias, scratch, p.cout, p.cin, 3, 3, p.cpg, p.ng, p.ncols, beta_dw, p.fuse_dbias);
+  NK_LAUNCHED(ctx, "conv_dw_finalize");
+  ctx->last_conv_kernel = "tcgen05_implicit_gemm_bwd_fused";
+  return NK_OK;
+}

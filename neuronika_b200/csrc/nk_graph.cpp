@@ -97,6 +97,7 @@ struct Gradient {
   std::shared_ptr<Gradient> alias;  // fusion: this gradient IS that gradient
   nkg_grad_hook hook = nullptr;     // data-parallel overlap: called when the last writer of a backward pass is done
   void* hook_user = nullptr;
+  int hook_chunks = 1;              // a matmul that is the last writer may deliver the gradient in this many row blocks
   int last_writer = -1;             // index (in reverse tape order) of the last node writing it in this pass
   bool hook_fired = false;
   Gradient(nk_ctx* c, Shape s, int dt) : ctx(c), shape(std::move(s)), dtype(dt) {}
@@ -178,7 +179,7 @@ static inline void grad_written(const GradientP& g) {
   Gradient* r = g->root();
   if (r->hook && r->last_writer == g_bwd_pos && !r->hook_fired) {
     r->hook_fired = true;
-    r->hook(r->hook_user);
+    r->hook(r->hook_user, 0, r->n());
   }
 }
 
@@ -243,11 +244,29 @@ struct MatMulBackward : Backward {
     if (right_grad) {
       float beta;
       void* d = right_grad->acc(&beta);
-      if (t)  // dW += G^T.X    : (M,N)^T.(M,K) -> (N,K)  TN
-        gemm(ctx, true, false, N, K, M, G, N, left_data->rptr(), K, beta, d, gdt, right_grad->dtype);
-      else    // dB += A^T.G    : (M,K)^T.(M,N) -> (K,N)  TN
-        gemm(ctx, true, false, K, N, M, left_data->rptr(), K, G, N, beta, d, gdt, right_grad->dtype);
-      grad_written(right_grad);
+      // TN in both cases: dW += G^T.X : (M,N)^T.(M,K) -> (N,K) | dB += A^T.G : (M,K)^T.(M,N) -> (K,N)
+      const void* A = t ? G : left_data->rptr();
+      const void* B = t ? left_data->rptr() : G;
+      const int64_t rows = t ? N : K, cols = t ? K : N;
+      Gradient* r = right_grad->root();
+      int chunks = 1;
+      if (r == right_grad.get() && r->hook && r->hook_chunks > 1 && r->last_writer == g_bwd_pos && !r->hook_fired &&
+          rows % (int64_t(r->hook_chunks) * 128) == 0)
+        chunks = r->hook_chunks;
+      if (chunks == 1) {
+        gemm(ctx, true, false, rows, cols, M, A, rows, B, cols, beta, d, gdt, right_grad->dtype);
+        grad_written(right_grad);
+      } else {
+        // row blocks of the gradient, each final (and handed to the hook) as soon as its GEMM is launched
+        const int64_t rc = rows / chunks;
+        for (int c = 0; c < chunks; ++c) {
+          const int64_t r0 = c * rc;
+          gemm(ctx, true, false, rc, cols, M, static_cast<const char*>(A) + r0 * esize(gdt), rows, B, cols, beta,
+               static_cast<char*>(d) + r0 * cols * esize(right_grad->dtype), gdt, right_grad->dtype);
+          r->hook(r->hook_user, r0 * cols, (r0 + rc) * cols);
+        }
+        r->hook_fired = true;
+      }
     }
     if (left_grad) {  // (M,K)
       float beta;
@@ -493,12 +512,6 @@ struct ConvolutionBackward : Backward {  // convolution/mod.rs:357-510: input fi
     if (bias_grad) out.push_back(bias_grad->root());
   }
   void backward() override {
-    if (input_grad) {
-      float beta;
-      void* d = input_grad->acc(&beta);
-      ck(ctx, nk_conv2d_bwd_input(ctx, d, gradient->get(), kernel->rptr(), a.n, a.cin, a.h, a.w, a.cout, a.kh, a.kw,
-                                  a.sh, a.sw, a.dh, a.dw, a.groups, gradient->dtype, beta));
-    }
     void* dbias = nullptr;
     if (bias_grad) {
       float bbeta;
@@ -513,7 +526,22 @@ struct ConvolutionBackward : Backward {  // convolution/mod.rs:357-510: input fi
                                    gradient->shape.data(), bbeta));
       }
     }
-    if (kernel_grad) {
+    if (input_grad && kernel_grad) {  // both halves: one pass over the output gradient where the kernels allow it
+      float bx, bw;
+      void* dxp = input_grad->acc(&bx);
+      void* dwp = kernel_grad->acc(&bw);
+      ck(ctx, nk_conv2d_bwd(ctx, dxp, bx, dwp, kernel_grad->dtype, dbias, bw, gradient->get(), input->rptr(),
+                            kernel->rptr(), a.n, a.cin, a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups,
+                            gradient->dtype));
+      grad_written(kernel_grad);
+      grad_written(input_grad);
+    } else if (input_grad) {
+      float beta;
+      void* d = input_grad->acc(&beta);
+      ck(ctx, nk_conv2d_bwd_input(ctx, d, gradient->get(), kernel->rptr(), a.n, a.cin, a.h, a.w, a.cout, a.kh, a.kw,
+                                  a.sh, a.sw, a.dh, a.dw, a.groups, gradient->dtype, beta));
+      grad_written(input_grad);
+    } else if (kernel_grad) {
       float beta;
       void* d = kernel_grad->acc(&beta);
       ck(ctx, nk_conv2d_bwd_kernel(ctx, d, kernel_grad->dtype, dbias, gradient->get(), input->rptr(), a.n, a.cin,
@@ -844,7 +872,7 @@ int nkg_backward(nkg_var* v, float seed) {
         for (Gradient* g : tg)
           if (g->hook && g->last_writer == pos && !g->hook_fired) {
             g->hook_fired = true;
-            g->hook(g->hook_user);
+            g->hook(g->hook_user, 0, g->n());
           }
       }
     }
@@ -1153,12 +1181,13 @@ int nkg_flatten(nkg_var* a, nkg_var** out) {
   });
 }
 
-int nkg_set_grad_hook(nkg_var* leaf, nkg_grad_hook cb, void* user) {
+int nkg_set_grad_hook(nkg_var* leaf, nkg_grad_hook cb, void* user, int row_chunks) {
   return guard([&] {
     if (!leaf || !leaf->diff()) fail(NK_ERR_INVALID_ARG, "nkg_set_grad_hook: not a differentiable variable");
     Gradient* r = leaf->grad->root();
     r->hook = cb;
     r->hook_user = user;
+    r->hook_chunks = row_chunks > 1 ? row_chunks : 1;
   });
 }
 

@@ -75,44 +75,87 @@ class GradientBucket:
             dist.all_reduce(t)
 
 
-class OverlappedAllReduce:
-    """All-reduce groups of leaf gradients (contiguous slices of a GradientBucket) on a side stream as soon as
-    backward has produced them, so the exchange overlaps the remaining backward kernels.
+class ReadyRanges:
+    """Bookkeeping of which element ranges of a gradient bucket are final during one backward pass.
 
-        sync = OverlappedAllReduce(bucket, compute_stream, groups=[[0, 1], [2, 3], [4, 5]], params=params)
-        loss.backward(1.0)        # hooks fire inside; every group's all-reduce is in flight when this returns
-        sync.wait()               # compute stream waits for the exchanges; then optimizer.step()
+    `add(lo, hi)` returns the ranges to exchange NOW: a range of at least `min_elems` goes out at once, widened by
+    any adjacent small pieces that were waiting (a bias next to the last block of its weight); small pieces wait for
+    such a neighbour.  `flush()` returns what is still waiting, merged where contiguous."""
+
+    def __init__(self, min_elems: int):
+        self.min_elems = int(min_elems)
+        self.held: List[Tuple[int, int]] = []
+
+    def add(self, lo: int, hi: int) -> List[Tuple[int, int]]:
+        if hi - lo < self.min_elems:
+            self.held.append((lo, hi))
+            return []
+        grown = True
+        while grown:
+            grown = False
+            for p in self.held:
+                if p[0] == hi:
+                    hi = p[1]
+                elif p[1] == lo:
+                    lo = p[0]
+                else:
+                    continue
+                self.held.remove(p)
+                grown = True
+                break
+        return [(lo, hi)]
+
+    def flush(self) -> List[Tuple[int, int]]:
+        out: List[Tuple[int, int]] = []
+        for lo, hi in sorted(self.held):
+            if out and out[-1][1] == lo:
+                out[-1] = (out[-1][0], hi)
+            else:
+                out.append((lo, hi))
+        self.held = []
+        return out
+
+
+class OverlappedAllReduce:
+    """All-reduce leaf gradients (slices of a GradientBucket) on a side stream as soon as backward has produced them,
+    so the exchange overlaps the remaining backward kernels.  Large matrices are delivered by the graph in row blocks
+    (`row_chunks`), so even a single layer's exchange overlaps its own dW GEMMs.
+
+        sync = OverlappedAllReduce(bucket, compute_stream, params)
+        loss.backward(1.0)        # hooks fire inside; the exchanges are in flight when this returns
+        sync.wait()               # flush what is left; compute stream waits for the exchanges; then optimizer.step()
     """
 
-    def __init__(self, bucket: GradientBucket, compute_stream, groups, params):
+    def __init__(self, bucket: GradientBucket, compute_stream, params, chunk_elems: int = 4 << 20,
+                 max_chunks: int = 8):
         import torch
         self.torch = torch
         self.bucket, self.compute, self.params = bucket, compute_stream, params
         self.comm = torch.cuda.Stream(device=bucket.array.device.index)
         self.event = torch.cuda.Event()
-        flat = bucket.as_torch()
-        self.groups = []
+        self.flat = bucket.as_torch()
+        self.ranges = ReadyRanges(min_elems=chunk_elems // 4)
+        self.launched = 0
         lay = bucket.layout
-        for g in groups:
-            lo = lay.offsets[g[0]]
-            last = g[-1]
-            hi = lay.offsets[last] + (int(np.prod(lay.shapes[last])) if lay.shapes[last] else 1)
-            self.groups.append({"members": list(g), "view": flat[lo:hi], "pending": len(g)})
-        for gi, g in enumerate(self.groups):
-            for pi in g["members"]:
-                params[pi].set_grad_hook(lambda gi=gi: self._ready(gi))
+        for pi, p in enumerate(params):
+            n = int(np.prod(lay.shapes[pi])) if lay.shapes[pi] else 1
+            chunks = max(1, min(max_chunks, n // chunk_elems))
+            p.set_grad_hook(lambda b, e, off=lay.offsets[pi]: self._ready(off + b, off + e), row_chunks=chunks)
 
-    def _ready(self, gi: int) -> None:
+    def _exchange(self, pieces) -> None:
         import torch.distributed as dist
-        g = self.groups[gi]
-        g["pending"] -= 1
-        if g["pending"] > 0:
+        if not pieces:
             return
-        g["pending"] = len(g["members"])
         self.event.record(self.compute)          # everything launched so far (incl. the kernels that wrote the grads)
         self.comm.wait_event(self.event)
         with self.torch.cuda.stream(self.comm):
-            dist.all_reduce(g["view"])
+            for lo, hi in pieces:
+                dist.all_reduce(self.flat[lo:hi])
+                self.launched += 1
+
+    def _ready(self, lo: int, hi: int) -> None:
+        self._exchange(self.ranges.add(lo, hi))
 
     def wait(self) -> None:
+        self._exchange(self.ranges.flush())
         self.compute.wait_stream(self.comm)

@@ -54,7 +54,7 @@ _G = {
     "nkg_convolution": (i32, [vp, vp, i64, i64, i64, i64, i64, pvp]),
     "nkg_flatten": (i32, [vp, pvp]),
     "nkg_sgd_step": (i32, [vp, vp, vp, f32, f32, f32, f32, i32, f32]),
-    "nkg_set_grad_hook": (i32, [vp, vp, vp]),
+    "nkg_set_grad_hook": (i32, [vp, vp, vp, i32]),
 }
 for _n, (_r, _a) in _G.items():
     _f = getattr(lib, _n)
@@ -62,7 +62,7 @@ for _n, (_r, _a) in _G.items():
     _f.argtypes = _a
 
 
-GRAD_HOOK = C.CFUNCTYPE(None, vp)
+GRAD_HOOK = C.CFUNCTYPE(None, vp, i64, i64)
 
 
 def graph_symbols():
@@ -234,16 +234,17 @@ class VarDiff(Var):
     def backward_history_len(self) -> int:
         return int(lib.nkg_backward_history_len(self._h))
 
-    def set_grad_hook(self, fn) -> None:
-        """Call `fn()` from inside backward() as soon as this leaf's gradient is final for the running pass
-        (used to overlap the data-parallel all-reduce with the rest of backward)."""
+    def set_grad_hook(self, fn, row_chunks: int = 1) -> None:
+        """Call `fn(begin, end)` from inside backward() as soon as elements [begin, end) of this leaf's gradient are
+        final for the running pass (used to overlap the data-parallel all-reduce with the rest of backward).  With
+        row_chunks > 1 a matmul backward that writes the gradient last delivers it in that many row blocks."""
         if fn is None:
             self._hook_ref = None
-            _ck(lib.nkg_set_grad_hook(self._h, None, None))
+            _ck(lib.nkg_set_grad_hook(self._h, None, None, 1))
             return
-        cb = GRAD_HOOK(lambda _user: fn())
+        cb = GRAD_HOOK(lambda _user, b, e: fn(int(b), int(e)))
         self._hook_ref = cb  # keep the trampoline alive
-        _ck(lib.nkg_set_grad_hook(self._h, C.cast(cb, vp), None))
+        _ck(lib.nkg_set_grad_hook(self._h, C.cast(cb, vp), None, int(row_chunks)))
 
 
 # ---- constructors (neuronika-variable/src/lib.rs:51-240), on a device

@@ -98,3 +98,32 @@ def test_two_rank_step_matches_single_process():
     # mean-reduced loss: the average of the two shard gradients equals the full-batch gradient
     for a, b in zip(got, want):
         assert np.allclose(a, b, rtol=1e-5, atol=1e-7)
+
+
+def test_ready_ranges_merges_small_pieces_with_neighbours():
+    """Host logic of the overlapped exchange: big row blocks go out at once and absorb adjacent small pieces
+    (the bias stored right after its weight); leftovers are flushed merged."""
+    from neuronika_b200.parallel import ReadyRanges
+    r = ReadyRanges(min_elems=100)
+    W, b = 400, 10                      # weight at [0, 400), bias at [400, 410), next bias at [410, 415)
+    assert r.add(W, W + b) == []        # bias first (its backward node runs before the matmul's)
+    assert r.add(0, 100) == [(0, 100)]
+    assert r.add(100, 200) == [(100, 200)]
+    assert r.add(200, 300) == [(200, 300)]
+    assert r.add(300, 400) == [(300, 410)]   # last block carries the bias
+    assert r.flush() == []
+    assert r.add(410, 415) == [] and r.add(415, 420) == [] and r.add(500, 505) == []
+    assert r.flush() == [(410, 420), (500, 505)]
+    assert r.flush() == []
+    # every element is exchanged exactly once whatever the arrival order
+    import itertools
+    pieces = [(0, 150), (150, 160), (160, 400), (400, 405)]
+    for order in itertools.permutations(pieces):
+        rr = ReadyRanges(min_elems=100)
+        out = []
+        for lo, hi in order:
+            out += rr.add(lo, hi)
+        out += rr.flush()
+        cover = sorted(out)
+        assert cover[0][0] == 0 and cover[-1][1] == 405
+        assert all(a[1] == b_[0] for a, b_ in zip(cover, cover[1:]))

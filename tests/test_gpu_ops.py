@@ -536,3 +536,52 @@ def test_conv2d_tensor_core_backward_input(nk, dev, O, shape, cout):
     ops.conv2d_bwd_input(dx1, dev.from_ndarray(g, nk.BF16), dev.from_ndarray(w, nk.BF16), beta=1.0)
     want1 = want + d0
     assert np.all(np.abs(dx1.as_ndarray() - want1) <= 2e-3 * scale + 2.0 ** -7 * np.abs(want1))
+
+
+@pytest.mark.parametrize("shape,cout", [((2, 3, 20, 24), 64), ((1, 3, 224, 224), 64), ((3, 1, 9, 40), 32),
+                                        ((2, 2, 70, 16), 16), ((2, 3, 130, 256), 64), ((5, 3, 120, 64), 128),
+                                        ((1, 3, 113, 24), 16)])
+def test_conv2d_tensor_core_backward_fused(nk, dev, O, shape, cout):
+    """ConvolutionBackward in one call (nk_conv2d_bwd): the output gradient is streamed once and feeds both the dW
+    (+ dbias) and the dX tensor-core chains.  Same contract as the two separate operators: accumulate with beta = 1,
+    overwrite with beta = 0; results agree with the oracle and with the unfused kernels; the halo rows a CTA recomputes
+    for dX must not be counted twice in dW (shapes taller than one row block)."""
+    import os
+    from neuronika_b200 import ops
+    rng = np.random.default_rng(14)
+    x = O.bf16_round(rnd(rng, shape, 0, 1))
+    w = O.bf16_round(rnd(rng, (cout, shape[1], 3, 3), -0.3, 0.3))
+    g = O.bf16_round(rnd(rng, (shape[0], cout, shape[2] - 2, shape[3] - 2)))
+    w0 = rnd(rng, w.shape)
+    b0 = rnd(rng, (cout, 1, 1))
+    d0 = O.bf16_round(rnd(rng, shape))
+    want_dx = np.zeros(shape, F32)
+    O.conv_backward_input(want_dx, g, w, (1, 1), (1, 1))
+    want_dw = np.zeros_like(w0)
+    O.conv_backward_kernel(want_dw, g, x, (1, 1), (1, 1))
+    want_db = g.astype(np.float64).sum((0, 2, 3)).reshape(cout, 1, 1)
+    sx = float(np.sqrt((want_dx.astype(np.float64) ** 2).mean())) + 1e-9
+    sw = float(np.sqrt((want_dw.astype(np.float64) ** 2).mean())) + 1e-9
+    G, X, Wd = dev.from_ndarray(g, nk.BF16), dev.from_ndarray(x, nk.BF16), dev.from_ndarray(w, nk.BF16)
+
+    dx, dw, db = dev.from_ndarray(d0, nk.BF16), dev.from_ndarray(w0, nk.F32), dev.from_ndarray(b0, nk.F32)
+    ops.conv2d_bwd(dx, dw, G, X, Wd, beta_dx=1.0, beta_dw=1.0, dbias=db)
+    assert dev.last_conv_kernel == "tcgen05_implicit_gemm_bwd_fused"
+    assert np.all(np.abs(dx.as_ndarray() - (want_dx + d0)) <= 2e-3 * sx + 2.0 ** -7 * np.abs(want_dx + d0))
+    assert np.all(np.abs(dw.as_ndarray() - (w0 + want_dw)) <= 2e-3 * sw + 1e-5)
+    assert np.all(np.abs(db.as_ndarray() - (b0 + want_db)) <= 2e-3 * (np.abs(want_db).max() + 1) + 1e-4)
+
+    dx2, dw2 = dev.from_ndarray(d0, nk.BF16), dev.from_ndarray(w0, nk.F32)   # overwrite mode, no dbias
+    ops.conv2d_bwd(dx2, dw2, G, X, Wd, beta_dx=0.0, beta_dw=0.0)
+    assert np.all(np.abs(dx2.as_ndarray() - want_dx) <= 2e-3 * sx + 2.0 ** -8 * np.abs(want_dx))
+    assert np.all(np.abs(dw2.as_ndarray() - want_dw) <= 2e-3 * sw + 1e-5)
+
+    os.environ["NK_CONV_UNFUSED_BWD"] = "1"    # the two separate tensor-core kernels: same dx bits, same dW to f32 noise
+    try:
+        dx3, dw3 = dev.from_ndarray(d0, nk.BF16), dev.from_ndarray(w0, nk.F32)
+        ops.conv2d_bwd(dx3, dw3, G, X, Wd, beta_dx=0.0, beta_dw=0.0)
+        assert dev.last_conv_kernel == "tcgen05_implicit_gemm_dx"
+    finally:
+        del os.environ["NK_CONV_UNFUSED_BWD"]
+    assert np.array_equal(dx3.as_ndarray(), dx2.as_ndarray())
+    assert np.all(np.abs(dw3.as_ndarray() - dw2.as_ndarray()) <= 1e-4 * sw + 1e-6)

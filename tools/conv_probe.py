@@ -3,6 +3,7 @@
     python tools/conv_probe.py fwd N C H W COUT KH KW [iters]
     python tools/conv_probe.py dw  N C H W COUT KH KW [iters]
     python tools/conv_probe.py dx  N C H W COUT KH KW [iters]
+    python tools/conv_probe.py bwd N C H W COUT KH KW [iters]     (dW + dbias + dX in one pass over G)
 """
 import json
 import os
@@ -50,6 +51,24 @@ def main():
             want = np.zeros_like(wt)
             O.conv_backward_kernel(want, g, x, (1, 1), (1, 1))
             want = want.astype(np.float64)
+            res["dbias_err"] = float(np.abs(db.as_ndarray().ravel() - g.astype(np.float64).sum((0, 2, 3))).max())
+    elif mode == "bwd":
+        out = nk.CuArray(dev, x.shape, nk.BF16)
+        odw = nk.CuArray(dev, wt.shape, nk.F32)
+        db = nk.CuArray(dev, (cout, 1, 1), nk.F32)
+        run = lambda: ops.conv2d_bwd(out, odw, dg_, dx_, dw_, beta_dx=0.0, beta_dw=0.0, dbias=db)
+        run()
+        dev.synchronize()
+        got = out.as_ndarray()
+        bytes_alg = 2.0 * (2 * x.size + g.size)
+        if check:
+            want = np.zeros_like(x)
+            O.conv_backward_input(want, g, wt, (1, 1), (1, 1))
+            want = want.astype(np.float64)
+            wdw = np.zeros_like(wt)
+            O.conv_backward_kernel(wdw, g, x, (1, 1), (1, 1))
+            res["dw_err"] = float(np.abs(odw.as_ndarray() - wdw).max())
+            res["dw_rms"] = float(np.sqrt((wdw.astype(np.float64) ** 2).mean()))
             res["dbias_err"] = float(np.abs(db.as_ndarray().ravel() - g.astype(np.float64).sum((0, 2, 3))).max())
     else:
         out = nk.CuArray(dev, x.shape, nk.BF16)
