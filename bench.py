@@ -272,7 +272,7 @@ def run_own(args):
     # produced it (gradient-ready hooks), overlapping the exchange with the remaining backward kernels
     sync = None
     if world > 1:
-        sync = OverlappedAllReduce(bucket, stream, params)
+        sync = OverlappedAllReduce(bucket, stream, params, max_chunks=int(os.environ.get("NK_DP_CHUNKS", "4")))
 
     def exchange_and_update():
         if sync is not None:
@@ -311,8 +311,10 @@ def run_own(args):
         l0 = dev.launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        h0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        timed.host_ms = (time.perf_counter() - h0) * 1e3 / steps   # host enqueue time per step (diagnostic)
         e1.record(stream)
         e1.synchronize()
         torch.cuda.synchronize()
@@ -329,6 +331,7 @@ def run_own(args):
 
     W_ = max(args.warmup, 3)
     ms, launches, clocks = timed(lambda: full_step(step_resident), args.steps, W_, sample_clocks=True)
+    host_ms = timed.host_ms
     if args.profile:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "profile_only": True, "ms_per_step": round(ms / args.steps, 5),
@@ -355,7 +358,7 @@ def run_own(args):
                            + (" -> sgd" if opt is not None else ""),
                    "l2": "working set per step exceeds the 126 MB L2 (no flush needed)",
                    "kernels": {"gemm": dev.last_gemm_kernel, "conv": dev.last_conv_kernel}},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 5), "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / e2e_steps, 5), "steps": e2e_steps,
                 "what": "pinned host -> HBM copy of the step inputs, forward, backward, loss read back, per step"},

@@ -304,7 +304,10 @@ int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
   }
   p.num_n_blocks = int((p.N + BLOCK_N - 1) / BLOCK_N);
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
-  int grid = num_tiles < ctx->sm_count ? num_tiles : ctx->sm_count;
+  // persistent grid balanced over the waves the tiles need anyway: 512 tiles on 148 SMs take 4 waves whether 148
+  // or 128 CTAs run them, and the 20 SMs left free let a concurrent NCCL all-reduce make progress
+  const int waves = (num_tiles + ctx->sm_count - 1) / ctx->sm_count;
+  int grid = (num_tiles + waves - 1) / waves;
   kern<<<grid, kNumThreads, C_::SMEM_BYTES, ctx->stream>>>(ta, tb, p);
   NK_LAUNCHED(ctx, "gemm_tcgen05");
   return NK_OK;
