@@ -138,7 +138,7 @@ def run_own(args):
 
     import neuronika_b200 as nk
     from neuronika_b200 import variable as V
-    from neuronika_b200.parallel import GradientBucket, OverlappedAllReduce
+    from neuronika_b200.parallel import FusedGradientExchange, GradientBucket, OverlappedAllReduce
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -159,9 +159,18 @@ def run_own(args):
     gdt = nk.F32 if args.grad_dtype == "f32" else nk.BF16
 
     # ---- parameters with gradients in ONE contiguous bucket (single all-reduce)
+    exchange_kind = os.environ.get("NK_DP_EXCHANGE", "fused") if world > 1 else "none"
+    if gdt != nk.F32 and exchange_kind == "fused":
+        exchange_kind = "nccl"       # the fused reduce-scatter epilogue sums f32 gradients
+    fused_exchange = []
+
     def make_bucket(shapes):
         if world == 1:      # no exchange step: let the graph own (and lazily clear) the gradients
             return None, [None] * len(shapes)
+        if exchange_kind == "fused":
+            ex = FusedGradientExchange(dev, stream, shapes, world, rank)
+            fused_exchange.append(ex)
+            return ex.bucket, ex.bucket.views
         b = GradientBucket(dev, shapes, gdt)
         return b, b.views
 
@@ -184,28 +193,30 @@ def run_own(args):
         x_host = drng.uniform(-1, 1, (n, fin)).astype(np.float32)
         t_host = drng.uniform(-1, 1, (n, fout)).astype(np.float32)
         x = V.from_ndarray(dev, x_host, BF).requires_grad()       # input as VarDiff => dX is computed
-        # device-resident step: root = y, backward(seed)
-        y = x.mm_t(W) + b
-        # e2e step: loss = mse(y, t)
         t = V.from_ndarray(dev, t_host, BF)
-        loss = y.mse_loss(t)
         host_inputs = [(pinned_bf16(x_host), x), (pinned_bf16(t_host), t)]
         opt = None
+        live = {}
 
-        def step_resident():
+        # every step builds its graph anew (define-by-run, as a user of the reference does each iteration: the op
+        # nodes and their intermediate tensors / gradients are fresh, the leaves persist)
+        def step_resident():            # root = y, backward(seed)
             for p in params:
                 p.zero_grad()
             x.zero_grad()
+            y = x.mm_t(W) + b
             y.forward()
             y.backward(1.0 / (n * fout))
+            live["root"] = y
 
-        def step_e2e_compute():
+        def step_e2e_compute():         # loss = mse(y, t)
             for p in params:
                 p.zero_grad()
             x.zero_grad()
+            loss = (x.mm_t(W) + b).mse_loss(t)
             loss.forward()
             loss.backward(1.0)
-        roots = (y, loss)
+            live["root"] = loss
     elif args.workload == "mlp":
         sizes, bsz = spec["sizes"], spec["batch"]
         shapes = []
@@ -221,23 +232,24 @@ def run_own(args):
         t_host = np.eye(10, dtype=np.float32)[np.argmax(x_host[:, :10], 1)]
         x = V.from_ndarray(dev, x_host, BF)
         t = V.from_ndarray(dev, t_host, BF)
-        h = x
-        for li in range(3):
-            h = h.mm_t(params[2 * li]) + params[2 * li + 1]
-            h = h.relu() if li < 2 else h.softmax(1)
-        loss = h.mse_loss(t)
         host_inputs = [(pinned_bf16(x_host), x), (pinned_bf16(t_host), t)]
         opt = nk.optim.StochasticGD.new(0.01, nk.optim.L2(0.0), grad_scale=1.0 / world,
                                         master_weights=args.master_weights)
         for p in params:
             opt.register(p)
+        live = {}
 
-        def step_resident():
+        def step_resident():            # a training iteration as written against the reference: new graph every step
             opt.zero_grad()
+            h = x
+            for li in range(3):
+                h = h.mm_t(params[2 * li]) + params[2 * li + 1]
+                h = h.relu() if li < 2 else h.softmax(1)
+            loss = h.mse_loss(t)
             loss.forward()
             loss.backward(1.0)
+            live["root"] = loss
         step_e2e_compute = step_resident
-        roots = (loss,)
     else:  # conv
         n, cin, hh, ww = spec["shape"]
         cout, ks = spec["cout"], spec["k"]
@@ -248,31 +260,37 @@ def run_own(args):
         params = [Wc, bc]
         x_host = drng.uniform(0, 1, (n, cin, hh, ww)).astype(np.float32)
         x = V.from_ndarray(dev, x_host, BF).requires_grad()
-        y = Wc.convolution(x, (1, 1), (1, 1), 1) + bc
-        loss = y.mean()
         host_inputs = [(pinned_bf16(x_host), x)]
         opt = None
+        live = {}
 
         def step_resident():
             for p in params:
                 p.zero_grad()
             x.zero_grad()
+            y = Wc.convolution(x, (1, 1), (1, 1), 1) + bc
             y.forward()
             y.backward(1.0 / 1e6)
+            live["root"] = y
 
         def step_e2e_compute():
             for p in params:
                 p.zero_grad()
             x.zero_grad()
+            loss = (Wc.convolution(x, (1, 1), (1, 1), 1) + bc).mean()
             loss.forward()
             loss.backward(1.0)
-        roots = (y, loss)
+            live["root"] = loss
 
     # N > 1: every layer's (W, b) slice of the bucket is all-reduced on a side stream as soon as backward has
     # produced it (gradient-ready hooks), overlapping the exchange with the remaining backward kernels
     sync = None
-    if world > 1:
-        sync = OverlappedAllReduce(bucket, stream, params, max_chunks=int(os.environ.get("NK_DP_CHUNKS", "4")))
+    if world > 1 and fused_exchange:
+        # the dW GEMM epilogue pushes gradient shards to their owners over NVLink; reduce + broadcast on a side stream
+        sync = fused_exchange[0]
+        sync.attach(params)
+    elif world > 1:
+        sync = OverlappedAllReduce(bucket, stream, params, max_chunks=int(os.environ.get("NK_DP_CHUNKS", "1")))
 
     def exchange_and_update():
         if sync is not None:
@@ -285,7 +303,6 @@ def run_own(args):
         exchange_and_update()
 
     loss_pinned = torch.empty((), dtype=torch.float32).pin_memory()
-    loss_t = as_torch(roots[-1].data_array(), torch, local)
 
     def e2e_step():
         with torch.cuda.stream(stream):
@@ -293,8 +310,9 @@ def run_own(args):
                 dst = as_torch(var.data_array(), torch, local)
                 dst.copy_(src.view(dst.shape), non_blocking=True)
         full_step(step_e2e_compute)
+        loss_t = as_torch(live["root"].data_array(), torch, local)     # this step's loss scalar
         with torch.cuda.stream(stream):
-            loss_pinned.copy_(loss_t, non_blocking=True)
+            loss_pinned.copy_(loss_t.view(()), non_blocking=True)
         stream.synchronize()
         return float(loss_pinned)
 
@@ -308,7 +326,7 @@ def run_own(args):
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
             sampler.start()
-        l0 = dev.launches
+        l0 = dev.launches + (sync.launches if hasattr(sync, 'launches') else 0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         h0 = time.perf_counter()
@@ -322,7 +340,7 @@ def run_own(args):
             dist.barrier()
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)
-        launches = dev.launches - l0
+        launches = dev.launches + (sync.launches if hasattr(sync, 'launches') else 0) - l0
         if world > 1:
             tt = torch.tensor([ms], device=f"cuda:{local}")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -353,8 +371,8 @@ def run_own(args):
         "warmup": W_, "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True,
         "scaling": spec["scaling"], "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "samples_per_s": round(spec["samples_per_rank_step"] * world / (ms / args.steps * 1e-3), 1),
-        "config": {"workload": spec["name"], "grad_dtype": args.grad_dtype, "parallelism": f"dp{world}",
-                   "step": "zero_grad -> forward -> backward" + (" (+ overlapped nccl all_reduce of each layer's grad slice)" if world > 1 else "")
+        "config": {"workload": spec["name"], "grad_dtype": args.grad_dtype, "parallelism": f"dp{world}", "exchange": exchange_kind,
+                   "step": "zero_grad -> forward -> backward" + ({"none": "", "nccl": " (+ overlapped nccl all_reduce of each layer's grad slice)", "fused": " (dW GEMM epilogue reduce-scatters over NVLink peer memory, owner reduce + broadcast on a side stream; nccl for the small tensors)"}[exchange_kind])
                            + (" -> sgd" if opt is not None else ""),
                    "l2": "working set per step exceeds the 126 MB L2 (no flush needed)",
                    "kernels": {"gemm": dev.last_gemm_kernel, "conv": dev.last_conv_kernel}},

@@ -69,6 +69,7 @@ const char* nk_last_gemm_kernel(nk_ctx* ctx);
 
 /* ---- buffers (replaces cuda::CuArray, cuda/cuarray.rs:10-171) ---- */
 int nk_alloc(nk_ctx* ctx, size_t bytes, void** dptr);      /* zero-filled, like CuArray::zeroed :35 */
+int nk_alloc_uninit(nk_ctx* ctx, size_t bytes, void** dptr); /* for buffers the next kernel fully overwrites */
 int nk_free(nk_ctx* ctx, void* dptr);
 int nk_h2d(nk_ctx* ctx, void* dst, const void* src, size_t bytes);   /* from_ndarray :114 */
 int nk_d2h(nk_ctx* ctx, void* dst, const void* src, size_t bytes);   /* as_ndarray :101 (blocks) */
@@ -178,6 +179,32 @@ const char* nk_last_conv_kernel(nk_ctx* ctx);
 int nk_sgd_step(nk_ctx* ctx, void* w, int w_dtype, void* g, int g_dtype, float* buf, float* master,
                 size_t n, float lr, float l2, float momentum, float dampening, int nesterov,
                 float grad_scale, int write_back_grad);
+
+/* ---- data-parallel gradient exchange over NVLink peer memory ----
+ * The reference has no multi-device path; under data parallel the only exchange on the hot path is
+ * the sum of the weight gradients over the replicas before the SGD step above (which then runs
+ * identically on every replica).  Rather than a library all-reduce after the dW GEMM, the exchange
+ * is fused into the kernels around it (neuronika_b200/csrc/nk_peer.cu):
+ *   nk_gemm_rs       the tcgen05 GEMM whose epilogue stores row shard o of the (M,N) f32 product
+ *                    into rank o's slot buffer `slots[o]` (world*M/world*N floats, slot index = the
+ *                    calling rank) over NVLink, tile by tile while the MMAs run (reduce-scatter);
+ *   nk_peer_barrier  flag exchange through peer memory: returns (on the stream) once every rank has
+ *                    reached the same `epoch`; `flags[r]` is rank r's flag array (>= world words);
+ *   nk_reduce_bcast  the owner sums its `world` slots in rank order and stores the result into every
+ *                    replica's gradient `grads[r]` at element rank*shard_elems (all-gather half).
+ * Buffers that peers touch come from nk_ipc_alloc (cudaMalloc; pool memory cannot be exported) and
+ * are mapped by the other processes with nk_ipc_export (64-byte handle) / nk_ipc_open. */
+int nk_ipc_alloc(nk_ctx* ctx, size_t bytes, void** out);
+int nk_ipc_free(nk_ctx* ctx, void* ptr);
+int nk_ipc_export(nk_ctx* ctx, void* ptr, void* handle64);
+int nk_ipc_open(nk_ctx* ctx, const void* handle64, void** peer_ptr);
+int nk_ipc_close(nk_ctx* ctx, void* peer_ptr);
+int nk_peer_barrier(nk_ctx* ctx, void* const* flags, int world, int rank, uint32_t epoch);
+int nk_gemm_rs(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha,
+               const void* A, int64_t lda, const void* B, int64_t ldb, void* const* slots, int world,
+               int rank, int ab_dtype);
+int nk_reduce_bcast(nk_ctx* ctx, const float* slots, void* const* grads, int world, int rank,
+                    int64_t shard_elems, int max_ctas);
 
 #ifdef __cplusplus
 }

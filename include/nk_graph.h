@@ -94,6 +94,13 @@ int nkg_flatten(nkg_var* a, nkg_var** out);
 typedef void (*nkg_grad_hook)(void* user, int64_t elem_begin, int64_t elem_end);
 int nkg_set_grad_hook(nkg_var* leaf, nkg_grad_hook cb, void* user, int row_chunks);
 
+/* ---- fused exchange (nk_b200.h "data-parallel gradient exchange"): when the matmul backward node that writes this
+ * leaf's gradient finds it all-zero (beta = 0), it runs nk_gemm_rs into `slots` instead of the plain dW GEMM and calls
+ * `cb(user, 1)`; otherwise (accumulating into an existing gradient, shape not shardable) it computes the gradient
+ * locally as usual and calls `cb(user, 0)` so that the caller can fall back to an all-reduce.  world <= 8. */
+typedef void (*nkg_grad_rs_hook)(void* user, int pushed);
+int nkg_set_grad_rs(nkg_var* leaf, int world, int rank, void* const* slots, nkg_grad_rs_hook cb, void* user);
+
 /* ---- SGD on a leaf (neuronika-optim/src/sgd/mod.rs:191-231) ---- */
 int nkg_sgd_step(nkg_var* param, float* momentum_buf, float* master, float lr, float l2, float momentum,
                  float dampening, int nesterov, float grad_scale);

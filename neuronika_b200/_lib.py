@@ -38,6 +38,7 @@ lib = C.CDLL(LIB_PATH)
 
 vp, i64, i32, f32, sz, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t, C.c_uint64
 pi64 = C.POINTER(C.c_int64)
+pvp = C.POINTER(C.c_void_p)
 
 _PROTOS = {
     "nk_ctx_create": (i32, [i32, C.POINTER(vp)]),
@@ -53,6 +54,7 @@ _PROTOS = {
     "nk_last_gemm_kernel": (C.c_char_p, [vp]),
     "nk_last_conv_kernel": (C.c_char_p, [vp]),
     "nk_alloc": (i32, [vp, sz, C.POINTER(vp)]),
+    "nk_alloc_uninit": (i32, [vp, sz, C.POINTER(vp)]),
     "nk_free": (i32, [vp, vp]),
     "nk_h2d": (i32, [vp, vp, vp, sz]),
     "nk_d2h": (i32, [vp, vp, vp, sz]),
@@ -87,6 +89,14 @@ _PROTOS = {
     "nk_conv2d_bwd_input": (i32, [vp, vp, vp, vp] + [i64] * 12 + [i32, f32]),
     "nk_conv2d_bwd": (i32, [vp, vp, f32, vp, i32, vp, f32, vp, vp, vp] + [i64] * 12 + [i32]),
     "nk_conv2d_bwd_kernel": (i32, [vp, vp, i32, vp, vp, vp] + [i64] * 12 + [i32, f32]),
+    "nk_ipc_alloc": (i32, [vp, sz, pvp]),
+    "nk_ipc_free": (i32, [vp, vp]),
+    "nk_ipc_export": (i32, [vp, vp, vp]),
+    "nk_ipc_open": (i32, [vp, vp, pvp]),
+    "nk_ipc_close": (i32, [vp, vp]),
+    "nk_peer_barrier": (i32, [vp, pvp, i32, i32, C.c_uint32]),
+    "nk_gemm_rs": (i32, [vp, i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, pvp, i32, i32, i32]),
+    "nk_reduce_bcast": (i32, [vp, vp, pvp, i32, i32, i64, i32]),
     "nk_sgd_step": (i32, [vp, vp, i32, vp, i32, vp, vp, sz, f32, f32, f32, f32, i32, f32, i32]),
 }
 

@@ -146,6 +146,15 @@ int nk_alloc(nk_ctx* ctx, size_t bytes, void** dptr) {
   return NK_OK;
 }
 
+int nk_alloc_uninit(nk_ctx* ctx, size_t bytes, void** dptr) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, dptr != nullptr, "nk_alloc_uninit: dptr is NULL");
+  *dptr = nullptr;
+  if (bytes == 0) bytes = 16;
+  NK_CUDA(ctx, cudaMallocAsync(dptr, bytes, ctx->stream));
+  return NK_OK;
+}
+
 int nk_free(nk_ctx* ctx, void* dptr) {
   if (!ctx) return NK_ERR_INVALID_ARG;
   if (!dptr) return NK_OK;

@@ -188,11 +188,47 @@ int launch(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K,
 // ------------------------------------------------------------------------------------------------------
 constexpr int kSkinnyMax = 16;
 
+// 4 consecutive elements of a row, as one 8-byte (bf16) or 16-byte (f32) access when `vec`, else scalars
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, bool vec, int valid, float* out) {
+  if (vec) {
+    if constexpr (sizeof(T) == 2) {
+      const uint2 w = *reinterpret_cast<const uint2*>(p);
+      out[0] = __uint_as_float(w.x << 16), out[1] = __uint_as_float(w.x & 0xffff0000u);
+      out[2] = __uint_as_float(w.y << 16), out[3] = __uint_as_float(w.y & 0xffff0000u);
+    } else {
+      const float4 w = *reinterpret_cast<const float4*>(p);
+      out[0] = w.x, out[1] = w.y, out[2] = w.z, out[3] = w.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = j < valid ? nk_to_f32<T>(p[j]) : 0.f;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, bool vec, int valid, const float* v) {
+  if (vec) {
+    if constexpr (sizeof(T) == 2) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 w;
+      w.x = *reinterpret_cast<uint32_t*>(&lo), w.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(p) = w;
+    } else {
+      *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < valid) p[j] = nk_from_f32<T>(v[j]);
+  }
+}
+
 template <typename TAB, typename TC>
 __global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
                                                            TC* __restrict__ C, int64_t M, int64_t N, int K,
                                                            int64_t lda, int64_t ldb, int64_t ldc, Epilogue ep) {
-  // block: 32 rows x 1024 columns; thread: 4 consecutive columns, all 32 rows
+  // block: 32 rows x 1024 columns; thread: 4 consecutive columns of all 32 rows, 4 rows in flight at a time so that
+  // the (optional) read of C and the stores overlap; every access to C is one 8/16-byte vector
   __shared__ float As[32][kSkinnyMax];
   const int64_t m0 = int64_t(blockIdx.y) * 32;
   const int64_t n = (int64_t(blockIdx.x) * 256 + threadIdx.x) * 4;
@@ -202,22 +238,51 @@ __global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict
   }
   __syncthreads();
   if (n >= N) return;
+  const int valid = int(N - n < 4 ? N - n : 4);
+  const bool vb = valid == 4 && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  const bool vc = valid == 4 && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
   float b[kSkinnyMax][4];
 #pragma unroll
-  for (int k = 0; k < kSkinnyMax; ++k)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) b[k][j] = (k < K && n + j < N) ? nk_to_f32<TAB>(B[int64_t(k) * ldb + n + j]) : 0.f;
-  for (int r = 0; r < 32 && m0 + r < M; ++r) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < kSkinnyMax; ++k) {
-      const float a = As[r][k];  // zero for k >= K
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, b[k][j], acc[j]);
-    }
+  for (int k = 0; k < kSkinnyMax; ++k) {
+    if (k < K) load4<TAB>(B + int64_t(k) * ldb + n, vb, valid, b[k]);
+    else b[k][0] = b[k][1] = b[k][2] = b[k][3] = 0.f;
+  }
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ep.bias) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (n + j < N) store_out<TC>(C, ldc, m0 + r, n + j, acc[j], ep);
+      if (j < valid)
+        bias[j] = ep.bias_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(ep.bias)[n + j])
+                               : static_cast<const float*>(ep.bias)[n + j];
+  }
+  const int rows = int(M - m0 < 32 ? M - m0 : 32);
+  for (int r0 = 0; r0 < rows; r0 += 4) {
+    float old[4][4];
+    if (ep.beta != 0.f) {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+        if (r0 + rr < rows) load4<TC>(C + (m0 + r0 + rr) * ldc + n, vc, valid, old[rr]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      if (r0 + rr >= rows) break;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < kSkinnyMax; ++k) {
+        const float a = As[r0 + rr][k];  // zero for k >= K
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, b[k][j], acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = ep.alpha * acc[j];
+        if (ep.beta != 0.f) v += ep.beta * old[rr][j];
+        v += bias[j];
+        if (ep.relu) v = v > 0.f ? v : 0.f;
+        acc[j] = v;
+      }
+      store4<TC>(C + (m0 + r0 + rr) * ldc + n, vc, valid, acc);
+    }
   }
 }
 
@@ -225,12 +290,15 @@ template <typename TAB>
 __global__ void __launch_bounds__(128) gemm_small_m_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
                                                            float* __restrict__ scratch, int M, int64_t N, int64_t K,
                                                            int64_t lda, int64_t ldb, int64_t k_per_block) {
-  // block: 512 columns (thread: 4 consecutive), one slab of k; A rows staged 64 at a time
+  // block: 512 columns (thread: 4 consecutive), one slab of k; A rows staged 64 at a time; the streamed operand B is
+  // read with one 8/16-byte load per (k, thread), 8 of them in flight
   __shared__ float As[64][kSkinnyMax];
   const int64_t n = (int64_t(blockIdx.x) * 128 + threadIdx.x) * 4;
   const int64_t k_begin = int64_t(blockIdx.y) * k_per_block;
   int64_t k_end = k_begin + k_per_block;
   if (k_end > K) k_end = K;
+  const int valid = n < N ? int(N - n < 4 ? N - n : 4) : 0;
+  const bool vb = valid == 4 && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
   float acc[kSkinnyMax][4];
 #pragma unroll
   for (int m = 0; m < kSkinnyMax; ++m)
@@ -243,26 +311,34 @@ __global__ void __launch_bounds__(128) gemm_small_m_kernel(const TAB* __restrict
       As[r][m] = (m < M && k0 + r < k_end) ? nk_to_f32<TAB>(A[(k0 + r) * lda + m]) : 0.f;
     }
     __syncthreads();
-    if (n < N) {
+    if (valid) {
       const int kk_end = int(k_end - k0 < 64 ? k_end - k0 : 64);
-      for (int kk = 0; kk < kk_end; ++kk) {
-        float bv[4];
+      for (int kb = 0; kb < kk_end; kb += 8) {
+        float bv[8][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bv[j] = (n + j < N) ? nk_to_f32<TAB>(B[(k0 + kk) * ldb + n + j]) : 0.f;
+        for (int u = 0; u < 8; ++u) {
+          if (kb + u < kk_end) load4<TAB>(B + (k0 + kb + u) * ldb + n, vb, valid, bv[u]);
+          else bv[u][0] = bv[u][1] = bv[u][2] = bv[u][3] = 0.f;
+        }
 #pragma unroll
-        for (int m = 0; m < kSkinnyMax; ++m) {
-          const float a = As[kk][m];
+        for (int u = 0; u < 8; ++u) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[m][j] = fmaf(a, bv[j], acc[m][j]);
+          for (int m = 0; m < kSkinnyMax; ++m) {
+            const float a = As[kb + u][m];   // rows >= kk_end of the slab are zero
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[m][j] = fmaf(a, bv[u][j], acc[m][j]);
+          }
         }
       }
     }
   }
-  if (n < N)
-    for (int m = 0; m < M; ++m)
+  if (valid) {
+#pragma unroll
+    for (int m = 0; m < kSkinnyMax; ++m)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (n + j < N) atomicAdd(&scratch[int64_t(m) * N + n + j], acc[m][j]);
+        if (m < M && j < valid) atomicAdd(&scratch[int64_t(m) * N + n + j], acc[m][j]);
+  }
 }
 
 template <typename TAB, typename TC>

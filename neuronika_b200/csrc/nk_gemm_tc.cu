@@ -40,7 +40,17 @@ struct GemmParams {
   // UMMA descriptor parameters (bytes)
   uint32_t a_lbo, a_sbo, a_kstep;
   uint32_t b_lbo, b_sbo, b_kstep;
+  // fused reduce-scatter epilogue (data parallel dW): rows [o*rs_rows, (o+1)*rs_rows) go to rs_dst[o]; the m-block
+  // order is rotated by m_rot so that the ranks do not all push to the same owner at the same time
+  int rs_world, m_rot;
+  int64_t rs_rows;
+  void* rs_dst[8];
 };
+
+__device__ __forceinline__ int tile_m_block(const GemmParams& p, int tile) {
+  int m = tile % p.num_m_blocks + p.m_rot;
+  return m >= p.num_m_blocks ? m - p.num_m_blocks : m;
+}
 
 template <int BLOCK_N>
 struct Cfg {
@@ -58,16 +68,45 @@ template <typename TC>
 __device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int64_t row, int64_t col0, const uint32_t* r,
                                                        int ncols, bool vec_ok) {
   TC* crow = static_cast<TC*>(p.C) + row * p.ldc + col0;
+  if (p.rs_world) {
+    const int owner = int(row / p.rs_rows);
+    crow = static_cast<TC*>(p.rs_dst[owner]) + (row - owner * p.rs_rows) * p.ldc + col0;
+  }
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(r[j]);
   const bool full = (col0 + 32 <= p.N) && ncols == 32;
   if (p.bias) {
+    // 32 scalar loads here serialise on L1 latency and made the epilogue slower than a K = 1024 main loop
+    // (profiles/r01_launches.md): fetch the 32 bias values of a full chunk with 16-byte loads
+    if (full && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+      if (p.bias_bf16) {
+        const uint4* bp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.bias) + col0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (col0 + j < p.N)
-        v[j] += p.bias_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[col0 + j])
-                            : static_cast<const float*>(p.bias)[col0 + j];
+        for (int q = 0; q < 4; ++q) {
+          const uint4 w = __ldg(bp + q);
+          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[q * 8 + 2 * i] += __uint_as_float(ww[i] << 16);
+            v[q * 8 + 2 * i + 1] += __uint_as_float(ww[i] & 0xffff0000u);
+          }
+        }
+      } else {
+        const float4* bp = reinterpret_cast<const float4*>(static_cast<const float*>(p.bias) + col0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 w = __ldg(bp + q);
+          v[q * 4] += w.x, v[q * 4 + 1] += w.y, v[q * 4 + 2] += w.z, v[q * 4 + 3] += w.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N)
+          v[j] += p.bias_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[col0 + j])
+                              : static_cast<const float*>(p.bias)[col0 + j];
+    }
   }
   if (full && vec_ok) {
     constexpr int V = 16 / sizeof(TC);
@@ -157,7 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_blocks, n_blk = tile / p.num_m_blocks;
+        const int m_blk = tile_m_block(p, tile), n_blk = tile / p.num_m_blocks;
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -226,7 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.num_m_blocks, n_blk = tile / p.num_m_blocks;
+      const int m_blk = tile_m_block(p, tile), n_blk = tile / p.num_m_blocks;
       const int64_t row = int64_t(m_blk) * BLOCK_M + q * 32 + lane;
       ptx::mbar_wait(tmem_full_bar(as), aphase);
       ptx::tc_fence_after();
@@ -379,6 +418,19 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   p.num_m_blocks = int((M + BLOCK_M - 1) / BLOCK_M);
   p.num_n_blocks = 0;
   p.num_k_blocks = int((K + BLOCK_K - 1) / BLOCK_K);
+  p.rs_world = 0;
+  p.m_rot = 0;
+  p.rs_rows = M;
+  for (int i = 0; i < 8; ++i) p.rs_dst[i] = nullptr;
+  if (ctx->rs_world > 1) {
+    if (M % (int64_t(ctx->rs_world) * BLOCK_M) != 0 || beta != 0.f || c_dtype != NK_F32)
+      return nk_set_error(ctx, NK_ERR_INVALID_ARG, "tcgen05 gemm: reduce-scatter epilogue needs M %% (world*128) == 0, "
+                          "beta == 0 and f32 output");
+    p.rs_world = ctx->rs_world;
+    p.rs_rows = M / ctx->rs_world;
+    p.m_rot = int(ctx->rs_rank * (p.rs_rows / BLOCK_M));
+    for (int i = 0; i < ctx->rs_world; ++i) p.rs_dst[i] = ctx->rs_dst[i];
+  }
   // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K.  MN-major: 64-wide chunks
   // BLOCK_K*128 B apart (LBO), 8-k groups 1024 B apart (SBO), +16 rows * 128 B per UMMA_K.
   p.a_lbo = a_mn ? BLOCK_K * 128 : 16;

@@ -72,15 +72,18 @@ struct Tensor {
     if (owned && ptr && !base) nk_free(ctx, ptr);
   }
   int64_t n() const { return numel(shape); }
-  // buffer about to be fully overwritten: no zero fill needed
+  // buffer about to be fully overwritten by a forward kernel: no zero fill needed
   void* wptr() {
     if (base) return base->wptr();
-    if (!ptr) {
-      ck(ctx, nk_alloc(ctx, size_t(n()) * esize(dtype), &ptr));  // nk_alloc zero-fills (CuArray::zeroed)
-    }
+    if (!ptr) ck(ctx, nk_alloc_uninit(ctx, size_t(n()) * esize(dtype), &ptr));
     return ptr;
   }
-  void* rptr() { return wptr(); }
+  // a reader of a tensor nothing has written yet sees zeros (CuArray::zeroed; test.rs:748-806 laziness checks)
+  void* rptr() {
+    if (base) return base->rptr();
+    if (!ptr) ck(ctx, nk_alloc(ctx, size_t(n()) * esize(dtype), &ptr));
+    return ptr;
+  }
 };
 using TensorP = std::shared_ptr<Tensor>;
 
@@ -98,6 +101,12 @@ struct Gradient {
   nkg_grad_hook hook = nullptr;     // data-parallel overlap: called when the last writer of a backward pass is done
   void* hook_user = nullptr;
   int hook_chunks = 1;              // a matmul that is the last writer may deliver the gradient in this many row blocks
+  int writers = 0;                  // backward nodes accumulating into it in the running pass
+  uint64_t pass_id = 0;
+  int rs_world = 0, rs_rank = 0;    // fused reduce-scatter plan (nkg_set_grad_rs)
+  void* rs_slots[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  nkg_grad_rs_hook rs_hook = nullptr;
+  void* rs_user = nullptr;
   int last_writer = -1;             // index (in reverse tape order) of the last node writing it in this pass
   bool hook_fired = false;
   Gradient(nk_ctx* c, Shape s, int dt) : ctx(c), shape(std::move(s)), dtype(dt) {}
@@ -126,6 +135,11 @@ struct Gradient {
   // known to be zero (then stale memory is simply overwritten), and the buffer counts as touched afterwards
   void* acc(float* beta) {
     Gradient* r = root();
+    if (r->enabled && !r->ptr) {  // first touch is a full overwrite (beta = 0): no need to clear the new buffer
+      ck(r->ctx, nk_alloc_uninit(r->ctx, size_t(r->n()) * esize(r->dtype), &r->ptr));
+      r->is_zero = true;
+      r->stale = false;
+    }
     if (!r->enabled || !r->ptr) get();
     *beta = r->is_zero ? 0.f : 1.f;
     r->is_zero = false;
@@ -250,10 +264,23 @@ struct MatMulBackward : Backward {
       const int64_t rows = t ? N : K, cols = t ? K : N;
       Gradient* r = right_grad->root();
       int chunks = 1;
-      if (r == right_grad.get() && r->hook && r->hook_chunks > 1 && r->last_writer == g_bwd_pos && !r->hook_fired &&
+      if (r->rs_world > 1) {
+        // data parallel: the epilogue of the dW GEMM pushes each row shard to its owner over NVLink (nk_gemm_rs);
+        // only when this node alone produces the gradient in this pass and the gradient starts from zero
+        const bool push = beta == 0.f && gdt == NK_BF16 && right_grad->dtype == NK_F32 && r == right_grad.get() &&
+                          r->writers == 1 && rows % (int64_t(r->rs_world) * 128) == 0;
+        if (push)
+          ck(ctx, nk_gemm_rs(ctx, 1, 0, rows, cols, M, 1.f, A, rows, B, cols, r->rs_slots, r->rs_world, r->rs_rank, gdt));
+        else
+          gemm(ctx, true, false, rows, cols, M, A, rows, B, cols, beta, d, gdt, right_grad->dtype);
+        if (r->rs_hook) r->rs_hook(r->rs_user, push ? 1 : 0);
+        chunks = 0;
+      } else if (r == right_grad.get() && r->hook && r->hook_chunks > 1 && r->last_writer == g_bwd_pos && !r->hook_fired &&
           rows % (int64_t(r->hook_chunks) * 128) == 0)
         chunks = r->hook_chunks;
-      if (chunks == 1) {
+      if (chunks == 0) {
+        // handled above
+      } else if (chunks == 1) {
         gemm(ctx, true, false, rows, cols, M, A, rows, B, cols, beta, d, gdt, right_grad->dtype);
         grad_written(right_grad);
       } else {
@@ -852,11 +879,19 @@ int nkg_backward(nkg_var* v, float seed) {
     std::vector<Gradient*> tg;
     bool any_hook = false;
     int pos = 0;
+    static thread_local uint64_t pass_counter = 0;
+    const uint64_t pass = ++pass_counter;
     for (auto it = v->bwd_buf.rbegin(); it != v->bwd_buf.rend(); ++it, ++pos) {
+      if ((*it)->skip) continue;
       tg.clear();
       (*it)->targets(tg);
       for (Gradient* g : tg)
-        if (g->hook) {
+        if (g->hook || g->rs_world > 1) {
+          if (g->pass_id != pass) {
+            g->pass_id = pass;
+            g->writers = 0;
+          }
+          ++g->writers;
           g->last_writer = pos;
           g->hook_fired = false;
           any_hook = true;
@@ -1178,6 +1213,20 @@ int nkg_flatten(nkg_var* a, nkg_var** out) {
     v->fwd_buf.clear();
     v->bwd_buf.clear();
     *out = v;
+  });
+}
+
+int nkg_set_grad_rs(nkg_var* leaf, int world, int rank, void* const* slots, nkg_grad_rs_hook cb, void* user) {
+  return guard([&] {
+    if (!leaf || !leaf->diff()) fail(NK_ERR_INVALID_ARG, "nkg_set_grad_rs: not a differentiable variable");
+    if (world < 0 || world > 8 || (world > 1 && (!slots || rank < 0 || rank >= world)))
+      fail(NK_ERR_INVALID_ARG, "nkg_set_grad_rs: bad world / rank");
+    Gradient* r = leaf->grad->root();
+    r->rs_world = world > 1 ? world : 0;
+    r->rs_rank = rank;
+    for (int i = 0; i < 8; ++i) r->rs_slots[i] = (world > 1 && i < world) ? slots[i] : nullptr;
+    r->rs_hook = world > 1 ? cb : nullptr;
+    r->rs_user = user;
   });
 }
 

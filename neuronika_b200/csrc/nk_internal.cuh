@@ -24,6 +24,10 @@ struct nk_ctx {
   const char* last_gemm_kernel = "none";
   const char* last_conv_kernel = "none";
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime
+  // reduce-scatter plan of the NEXT tcgen05 GEMM (set by nk_gemm_rs around its call): row shard o of the product is
+  // stored to rs_dst[o] (rank o's slot buffer, peer-mapped, already offset to this rank's slot) instead of C
+  int rs_world = 0, rs_rank = 0;
+  void* rs_dst[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 int nk_set_error(nk_ctx* ctx, int code, const char* fmt, ...);

@@ -1,0 +1,160 @@
+// nk_peer.cu -- data-parallel gradient exchange over NVLink peer memory.
+//
+// The reference has no multi-device path; the hot path's only exchange step is the sum of the weight gradients over
+// the replicas before the SGD step (neuronika-optim/src/sgd/mod.rs:191-231 then runs identically on every replica).
+// Instead of calling a library all-reduce after the dW GEMM, the exchange is fused into the kernels around it:
+//   1. reduce-scatter inside the GEMM epilogue: nk_gemm_rs runs the tcgen05 dW GEMM, and the epilogue stores row shard
+//      o of the local product straight into rank o's slot buffer over NVLink (slot index = this rank) -- the transfer
+//      overlaps the MMAs tile by tile and the local gradient is never written to local HBM;
+//   2. nk_peer_barrier: flag exchange through peer memory (all pushes landed);
+//   3. nk_reduce_bcast: the owner sums its `world` slots in rank order (so every replica receives bit-identical sums)
+//      and stores the result into EVERY replica's gradient buffer over NVLink (the all-gather half);
+//   4. nk_peer_barrier again, then the ordinary nk_sgd_step on every replica.
+// Memory that peers touch comes from nk_ipc_alloc (plain cudaMalloc: CUDA IPC cannot export pool memory) and is
+// mapped into the other processes with nk_ipc_export / nk_ipc_open.
+#include "nk_internal.cuh"
+
+#include <cstring>
+
+namespace {
+
+constexpr int kMaxWorld = 8;
+
+struct PeerPtrs {
+  void* p[kMaxWorld];
+};
+
+// one thread per peer: publish `epoch` in the peer's flag array, then wait for the peer's epoch in our own
+__global__ void peer_barrier_kernel(PeerPtrs flags, int world, int rank, uint32_t epoch, int* error) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  __threadfence_system();
+  volatile uint32_t* theirs = static_cast<uint32_t*>(flags.p[r]) + rank;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+  const uint32_t* mine = static_cast<const uint32_t*>(flags.p[rank]) + r;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (int32_t(v - epoch) >= 0) break;
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer died; fail loudly instead of hanging the GPU
+      *error = 1;
+      __trap();
+    }
+    __nanosleep(64);
+  }
+  __threadfence_system();
+}
+
+// out[e] = sum_s slots[s][e] (rank order), stored to every replica's gradient at `offset + e`
+__global__ void __launch_bounds__(1024) reduce_bcast_kernel(const float4* __restrict__ slots, PeerPtrs grads, int world,
+                                                            int64_t shard_vec, int64_t offset_vec) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < shard_vec; i += stride) {
+    float4 acc = __ldcs(slots + i);
+    for (int s = 1; s < world; ++s) {
+      const float4 v = __ldcs(slots + s * shard_vec + i);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    for (int r = 0; r < world; ++r) static_cast<float4*>(grads.p[r])[offset_vec + i] = acc;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int nk_ipc_alloc(nk_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return NK_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (bytes == 0) return NK_OK;
+  NK_CUDA(ctx, cudaMalloc(out, bytes));
+  NK_CUDA(ctx, cudaMemsetAsync(*out, 0, bytes, ctx->stream));
+  NK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NK_OK;
+}
+
+int nk_ipc_free(nk_ctx* ctx, void* ptr) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  if (ptr) NK_CUDA(ctx, cudaFree(ptr));
+  return NK_OK;
+}
+
+int nk_ipc_export(nk_ctx* ctx, void* ptr, void* handle64) {
+  if (!ctx || !ptr || !handle64) return NK_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  NK_CUDA(ctx, cudaIpcGetMemHandle(&h, ptr));
+  memcpy(handle64, &h, 64);
+  return NK_OK;
+}
+
+int nk_ipc_open(nk_ctx* ctx, const void* handle64, void** out) {
+  if (!ctx || !handle64 || !out) return NK_ERR_INVALID_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  NK_CUDA(ctx, cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return NK_OK;
+}
+
+int nk_ipc_close(nk_ctx* ctx, void* peer_ptr) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  if (peer_ptr) NK_CUDA(ctx, cudaIpcCloseMemHandle(peer_ptr));
+  return NK_OK;
+}
+
+int nk_peer_barrier(nk_ctx* ctx, void* const* flags, int world, int rank, uint32_t epoch) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, flags && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world,
+             "nk_peer_barrier: bad world %d / rank %d", world, rank);
+  PeerPtrs f;
+  for (int i = 0; i < kMaxWorld; ++i) f.p[i] = i < world ? flags[i] : nullptr;
+  int* err;
+  int rc = nk_workspace(ctx, 256, (void**)&err);
+  if (rc) return rc;
+  peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(f, world, rank, epoch, err);
+  NK_LAUNCHED(ctx, "peer_barrier");
+  return NK_OK;
+}
+
+int nk_reduce_bcast(nk_ctx* ctx, const float* slots, void* const* grads, int world, int rank, int64_t shard_elems,
+                    int max_ctas) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, slots && grads && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world,
+             "nk_reduce_bcast: bad arguments");
+  NK_REQUIRE(ctx, shard_elems % 4 == 0, "nk_reduce_bcast: shard of %lld elements is not a multiple of 4",
+             (long long)shard_elems);
+  if (shard_elems == 0) return NK_OK;
+  PeerPtrs g;
+  for (int i = 0; i < kMaxWorld; ++i) g.p[i] = i < world ? grads[i] : nullptr;
+  const int64_t vec = shard_elems / 4;
+  int grid = max_ctas > 0 ? max_ctas : 20;
+  if (int64_t(grid) * 1024 > vec) grid = int((vec + 1023) / 1024);
+  reduce_bcast_kernel<<<grid, 1024, 0, ctx->stream>>>(reinterpret_cast<const float4*>(slots), g, world, vec,
+                                                      int64_t(rank) * vec);
+  NK_LAUNCHED(ctx, "reduce_bcast");
+  return NK_OK;
+}
+
+int nk_gemm_rs(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
+               int64_t lda, const void* B, int64_t ldb, void* const* slots, int world, int rank, int ab_dtype) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, slots && world >= 2 && world <= kMaxWorld && rank >= 0 && rank < world,
+             "nk_gemm_rs: bad world %d / rank %d", world, rank);
+  NK_REQUIRE(ctx, ab_dtype == NK_BF16, "nk_gemm_rs: the fused exchange runs on the tcgen05 engine (bf16 operands)");
+  NK_REQUIRE(ctx, M % (int64_t(world) * 128) == 0, "nk_gemm_rs: M = %lld is not a multiple of world * 128",
+             (long long)M);
+  const int64_t shard = (M / world) * N;  // elements per (owner, source) slot
+  ctx->rs_world = world;
+  ctx->rs_rank = rank;
+  for (int o = 0; o < world; ++o) ctx->rs_dst[o] = static_cast<float*>(slots[o]) + int64_t(rank) * shard;
+  const int saved = ctx->gemm_engine;
+  ctx->gemm_engine = NK_GEMM_TCGEN05;
+  const int rc = nk_gemm_bias_act(ctx, transA, transB, M, N, K, alpha, A, lda, B, ldb, 0.f, ctx->rs_dst[rank], N, ab_dtype,
+                                  NK_F32, nullptr, NK_F32, 0);
+  ctx->gemm_engine = saved;
+  ctx->rs_world = 0;
+  return rc;
+}
+
+}  // extern "C"

@@ -43,10 +43,10 @@ class GradientBucket:
     """One contiguous device buffer holding every leaf gradient; `views[i]` is handed to
     `Var.requires_grad(grad_array=...)` so backward writes straight into the bucket."""
 
-    def __init__(self, device, shapes, dtype):
+    def __init__(self, device, shapes, dtype, ptr=None):
         from .device import CuArray
         self.layout = BucketLayout(shapes)
-        self.array = CuArray(device, (self.layout.total,), dtype)
+        self.array = CuArray(device, (self.layout.total,), dtype, ptr=ptr)   # ptr: caller-owned (peer-mapped) memory
         self.views = [self.array.slice_flat(o, s) for s, o in zip(self.layout.shapes, self.layout.offsets)]
         self._torch = None
 
@@ -158,4 +158,143 @@ class OverlappedAllReduce:
 
     def wait(self) -> None:
         self._exchange(self.ranges.flush())
+        self.compute.wait_stream(self.comm)
+
+
+class PeerMemory:
+    """Device buffers every rank can address (nk_ipc_alloc + CUDA IPC handles exchanged through the process group):
+    `ptrs[r]` is rank r's buffer as seen from THIS process (ptrs[rank] is the local allocation)."""
+
+    def __init__(self, device, nbytes: int, world: int, rank: int):
+        import ctypes as C
+        import torch.distributed as dist
+        from . import _lib as L
+        self.device, self.world, self.rank, self.nbytes = device, world, rank, int(nbytes)
+        p = C.c_void_p()
+        L.check(L.lib.nk_ipc_alloc(device.ctx, self.nbytes, C.byref(p)), device.ctx)
+        self.local = int(p.value)
+        h = C.create_string_buffer(64)
+        L.check(L.lib.nk_ipc_export(device.ctx, C.c_void_p(self.local), h), device.ctx)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(h.raw))
+        self.ptrs: List[int] = []
+        for r in range(world):
+            if r == rank:
+                self.ptrs.append(self.local)
+            else:
+                q = C.c_void_p()
+                L.check(L.lib.nk_ipc_open(device.ctx, C.create_string_buffer(handles[r], 64), C.byref(q)), device.ctx)
+                self.ptrs.append(int(q.value))
+        self.table = (C.c_void_p * world)(*self.ptrs)
+
+    def offset_table(self, byte_offset: int):
+        import ctypes as C
+        return (C.c_void_p * self.world)(*[p + int(byte_offset) for p in self.ptrs])
+
+
+def rs_eligible(shape, world: int, min_elems: int = 1 << 20) -> bool:
+    """A parameter takes the fused exchange when it is a matrix whose rows split into world shards of 128-row GEMM
+    tiles (nk_gemm_rs) and it is big enough for the exchange to matter; the rest goes through the all-reduce."""
+    if len(shape) != 2 or world < 2:
+        return False
+    rows, cols = int(shape[0]), int(shape[1])
+    return rows % (world * 128) == 0 and rows * cols >= min_elems and (rows // world * cols) % 4 == 0
+
+
+class FusedGradientExchange:
+    """Data-parallel gradient exchange with the reduce-scatter fused into the dW GEMM (nk_gemm_rs) for the large
+    matrices, and the NCCL all-reduce for everything else (biases, small or oddly shaped matrices).
+
+        ex = FusedGradientExchange(device, compute_stream, shapes, world, rank)     # owns the gradient bucket
+        params = [from_ndarray(...).requires_grad(F32, ex.bucket.views[i]) for i ...]
+        ex.attach(params)
+        loss.backward(1.0)      # dW epilogues push shards to their owners; reduce + broadcast run on a side stream
+        ex.wait()               # all gradients (summed over ranks) are in the bucket; then optimizer.step()
+
+    Per large matrix and step, on the side stream: barrier (all pushes landed) -> nk_reduce_bcast (the owner sums its
+    `world` slots in rank order and stores the sums into every replica's bucket) -> barrier (all sums landed).  Every
+    replica receives bit-identical gradients."""
+
+    def __init__(self, device, compute_stream, shapes, world: int, rank: int, reduce_ctas: int = 20,
+                 min_elems: int = 1 << 20):
+        import torch
+        from .device import F32
+        self.torch, self.device, self.compute = torch, device, compute_stream
+        self.world, self.rank, self.reduce_ctas = world, rank, reduce_ctas
+        self.layout = BucketLayout(shapes)
+        self.bucket_mem = PeerMemory(device, self.layout.total * 4, world, rank)
+        self.bucket = GradientBucket(device, shapes, F32, ptr=self.bucket_mem.local)
+        self.fused = [i for i, s in enumerate(self.layout.shapes) if rs_eligible(s, world, min_elems)]
+        self.slot_off = {}
+        off = 0
+        for i in self.fused:
+            self.slot_off[i] = off
+            off += int(np.prod(self.layout.shapes[i]))
+        self.slots = PeerMemory(device, max(off, 4) * 4, world, rank)
+        self.flags = PeerMemory(device, 256, world, rank)
+        self.epoch = 0
+        self.comm = torch.cuda.Stream(device=device.index)
+        self.event = torch.cuda.Event()
+        self.ranges = ReadyRanges(min_elems=1 << 62)      # everything that is not fused waits for wait()
+        self.flat = self.bucket.as_torch()
+        self.pushed = 0
+        self.comm_device = None
+
+    def attach(self, params) -> None:
+        from .device import Device
+        # the side stream gets its own context handle bound to the same device: kernels are enqueued on self.comm
+        self.comm_device = Device(self.device.index, stream=self.comm.cuda_stream)
+        lay = self.layout
+        for pi, p in enumerate(params):
+            if pi in self.fused:
+                table = self.slots.offset_table(self.slot_off[pi] * 4)
+                p.set_grad_rs(self.world, self.rank, [int(v) for v in table],
+                              lambda pushed, pi=pi: self._pushed(pi, pushed))
+            else:
+                n = int(np.prod(lay.shapes[pi])) if lay.shapes[pi] else 1
+                p.set_grad_hook(lambda b, e, off=lay.offsets[pi]: self.ranges.add(off + b, off + e))
+
+    def _barrier(self) -> None:
+        from . import _lib as L
+        self.epoch += 1
+        L.check(L.lib.nk_peer_barrier(self.comm_device.ctx, self.flags.table, self.world, self.rank, self.epoch),
+                self.comm_device.ctx)
+
+    def _pushed(self, pi: int, pushed: int) -> None:
+        from . import _lib as L
+        import ctypes as C
+        lay = self.layout
+        n = int(np.prod(lay.shapes[pi]))
+        if not pushed:                                  # computed locally: plain all-reduce of that range
+            self.ranges.held.append((lay.offsets[pi], lay.offsets[pi] + n))
+            return
+        self.pushed += 1
+        self.event.record(self.compute)                 # the dW GEMM (and its pushes) launched so far
+        self.comm.wait_event(self.event)
+        shard = n // self.world
+        self._barrier()
+        grads = self.bucket_mem.offset_table(lay.offsets[pi] * 4)
+        slots_local = self.slots.local + self.slot_off[pi] * 4
+        L.check(L.lib.nk_reduce_bcast(self.comm_device.ctx, C.c_void_p(slots_local), grads, self.world, self.rank, shard,
+                                      self.reduce_ctas), self.comm_device.ctx)
+        self._barrier()
+        self._all_reduce_rest()      # biases etc. that became ready meanwhile ride behind it on the side stream
+
+    def _all_reduce_rest(self) -> None:
+        import torch.distributed as dist
+        rest = self.ranges.flush()
+        if rest:
+            with self.torch.cuda.stream(self.comm):
+                for lo, hi in rest:
+                    dist.all_reduce(self.flat[lo:hi])
+
+    @property
+    def launches(self) -> int:
+        return self.comm_device.launches if self.comm_device is not None else 0
+
+    def wait(self) -> None:
+        if self.ranges.held:
+            self.event.record(self.compute)
+            self.comm.wait_event(self.event)
+            self._all_reduce_rest()
         self.compute.wait_stream(self.comm)

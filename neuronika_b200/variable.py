@@ -55,6 +55,7 @@ _G = {
     "nkg_flatten": (i32, [vp, pvp]),
     "nkg_sgd_step": (i32, [vp, vp, vp, f32, f32, f32, f32, i32, f32]),
     "nkg_set_grad_hook": (i32, [vp, vp, vp, i32]),
+    "nkg_set_grad_rs": (i32, [vp, i32, i32, pvp, vp, vp]),
 }
 for _n, (_r, _a) in _G.items():
     _f = getattr(lib, _n)
@@ -63,6 +64,7 @@ for _n, (_r, _a) in _G.items():
 
 
 GRAD_HOOK = C.CFUNCTYPE(None, vp, i64, i64)
+GRAD_RS_HOOK = C.CFUNCTYPE(None, vp, i32)
 
 
 def graph_symbols():
@@ -245,6 +247,20 @@ class VarDiff(Var):
         cb = GRAD_HOOK(lambda _user, b, e: fn(int(b), int(e)))
         self._hook_ref = cb  # keep the trampoline alive
         _ck(lib.nkg_set_grad_hook(self._h, C.cast(cb, vp), None, int(row_chunks)))
+
+
+    def set_grad_rs(self, world: int, rank: int, slot_ptrs, fn) -> None:
+        """Fused data-parallel exchange (nk_b200.h nk_gemm_rs): the matmul backward node that produces this leaf's
+        gradient pushes row shard o of its product into `slot_ptrs[o]` (rank o's slot buffer, peer-mapped) and then
+        calls `fn(pushed)`; pushed == 0 means the gradient was computed locally (caller falls back to all-reduce)."""
+        if world <= 1:
+            self._rs_ref = None
+            _ck(lib.nkg_set_grad_rs(self._h, 0, 0, None, None, None))
+            return
+        arr = (vp * world)(*[int(p) for p in slot_ptrs])
+        cb = GRAD_RS_HOOK(lambda _user, pushed: fn(int(pushed)))
+        self._rs_ref = (cb, arr)
+        _ck(lib.nkg_set_grad_rs(self._h, int(world), int(rank), arr, C.cast(cb, vp), None))
 
 
 # ---- constructors (neuronika-variable/src/lib.rs:51-240), on a device

@@ -127,3 +127,13 @@ def test_ready_ranges_merges_small_pieces_with_neighbours():
         cover = sorted(out)
         assert cover[0][0] == 0 and cover[-1][1] == 405
         assert all(a[1] == b_[0] for a, b_ in zip(cover, cover[1:]))
+
+
+def test_fused_exchange_eligibility():
+    """which parameters take the fused reduce-scatter GEMM epilogue: matrices whose rows split into world shards of
+    whole 128-row tiles; biases, the 10-wide output layer and conv kernels stay on the all-reduce"""
+    from neuronika_b200.parallel import rs_eligible
+    assert rs_eligible((4096, 4096), 2) and rs_eligible((4096, 4096), 8) and rs_eligible((4096, 1024), 8)
+    assert not rs_eligible((4096,), 2) and not rs_eligible((10, 4096), 2) and not rs_eligible((64, 3, 3, 3), 2)
+    assert not rs_eligible((4096, 4096), 1) and not rs_eligible((384, 4096), 2)      # 192 rows per rank: not whole tiles
+    assert not rs_eligible((256, 256), 2)                                             # too small to matter
