@@ -168,7 +168,8 @@ def run_own(args):
         if world == 1:      # no exchange step: let the graph own (and lazily clear) the gradients
             return None, [None] * len(shapes)
         if exchange_kind == "fused":
-            ex = FusedGradientExchange(dev, stream, shapes, world, rank)
+            ex = FusedGradientExchange(dev, stream, shapes, world, rank,
+                                       reduce_ctas=int(os.environ.get("NK_DP_REDUCE_CTAS", "20")))
             fused_exchange.append(ex)
             return ex.bucket, ex.bucket.views
         b = GradientBucket(dev, shapes, gdt)

@@ -26,6 +26,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 192;
+constexpr int kRsPitch = 36;                        // floats per staged row (conflict-free 16-byte accesses)
+constexpr uint32_t kRsStageBytes = 4 * 32 * kRsPitch * 4;  // 4 epilogue warps x 32 rows
 constexpr uint32_t kSmemLimit = 232448;  // 227 KB
 
 struct GemmParams {
@@ -40,16 +42,20 @@ struct GemmParams {
   // UMMA descriptor parameters (bytes)
   uint32_t a_lbo, a_sbo, a_kstep;
   uint32_t b_lbo, b_sbo, b_kstep;
-  // fused reduce-scatter epilogue (data parallel dW): rows [o*rs_rows, (o+1)*rs_rows) go to rs_dst[o]; the m-block
-  // order is rotated by m_rot so that the ranks do not all push to the same owner at the same time
+  // fused reduce-scatter epilogue (data parallel dW): rows [o*rs_rows, (o+1)*rs_rows) go to rs_dst[o]; m_rot = rank
+  // staggers the owner order between ranks (tile_m_block)
   int rs_world, m_rot;
   int64_t rs_rows;
   void* rs_dst[8];
 };
 
 __device__ __forceinline__ int tile_m_block(const GemmParams& p, int tile) {
-  int m = tile % p.num_m_blocks + p.m_rot;
-  return m >= p.num_m_blocks ? m - p.num_m_blocks : m;
+  const int t = tile % p.num_m_blocks;
+  if (p.rs_world == 0) return t;
+  // consecutive tiles go to consecutive owners (starting with a different one on every rank), so that the remote
+  // stores are spread evenly over the whole kernel and over all links instead of bunching up at the end
+  const int owner = (t + p.m_rot) % p.rs_world;
+  return owner * (p.num_m_blocks / p.rs_world) + t / p.rs_world;
 }
 
 template <int BLOCK_N>
@@ -262,6 +268,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // ===================================================== epilogue (4 warps)
     const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
     const bool vec_ok = ((p.ldc * int64_t(sizeof(TC))) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    float* rs_stage = reinterpret_cast<float*>(smem_raw + (bar_base + 512 - ptx::smem_u32(smem_raw)));
+    (void)rs_stage;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -277,6 +285,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
           ptx::tmem_ld_wait();
           const int64_t col0 = int64_t(n_blk) * BLOCK_N + c * 32;
+          if constexpr (sizeof(TC) == 4 && BLOCK_N == 256) {
+            if (p.rs_world) {
+              // reduce-scatter epilogue: the chunk goes to the owner's slot over NVLink.  One thread per row would
+              // emit 16-byte packets; transpose the 32x32 chunk through shared memory so that every store
+              // instruction writes four full 128-byte row segments.
+              float* stg = rs_stage + (warp_idx - 2) * (32 * kRsPitch);
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq)
+                *reinterpret_cast<float4*>(stg + lane * kRsPitch + qq * 4) =
+                    make_float4(p.alpha * __uint_as_float(r[qq * 4]), p.alpha * __uint_as_float(r[qq * 4 + 1]),
+                                p.alpha * __uint_as_float(r[qq * 4 + 2]), p.alpha * __uint_as_float(r[qq * 4 + 3]));
+              __syncwarp();
+              const int64_t row0 = int64_t(m_blk) * BLOCK_M + q * 32;
+              const int owner = int(row0 / p.rs_rows);   // a 128-row tile never straddles two shards
+              float* dst0 = static_cast<float*>(p.rs_dst[owner]) + (row0 - owner * p.rs_rows) * p.ldc + col0 + (lane & 7) * 4;
+              const bool col_ok = col0 + (lane & 7) * 4 < p.N;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + (lane >> 3);
+                const float4 v = *reinterpret_cast<const float4*>(stg + rr * kRsPitch + (lane & 7) * 4);
+                if (col_ok && row0 + rr < p.M) *reinterpret_cast<float4*>(dst0 + int64_t(rr) * p.ldc) = v;
+              }
+              __syncwarp();
+              continue;
+            }
+          }
           if (row < p.M && col0 < p.N) epilogue_store_chunk32<TC>(p, row, col0, r, 32, vec_ok);
         }
       } else {
@@ -338,7 +372,8 @@ int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
   auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, TC>;
   static bool attr_done = false;  // per template instantiation
   if (!attr_done) {
-    NK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM_BYTES));
+    const uint32_t max_smem = C_::SMEM_BYTES + kRsStageBytes <= kSmemLimit ? C_::SMEM_BYTES + kRsStageBytes : C_::SMEM_BYTES;
+    NK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
     attr_done = true;
   }
   p.num_n_blocks = int((p.N + BLOCK_N - 1) / BLOCK_N);
@@ -347,7 +382,13 @@ int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
   // or 128 CTAs run them, and the 20 SMs left free let a concurrent NCCL all-reduce make progress
   const int waves = (num_tiles + ctx->sm_count - 1) / ctx->sm_count;
   int grid = (num_tiles + waves - 1) / waves;
-  kern<<<grid, kNumThreads, C_::SMEM_BYTES, ctx->stream>>>(ta, tb, p);
+  size_t smem = C_::SMEM_BYTES;
+  if (p.rs_world) {
+    if (BLOCK_N != 256 || sizeof(TC) != 4 || p.N % 4 != 0)
+      return nk_set_error(ctx, NK_ERR_UNSUPPORTED, "tcgen05 gemm: reduce-scatter epilogue needs 128x256 tiles, f32, N %% 4 == 0");
+    smem += kRsStageBytes;
+  }
+  kern<<<grid, kNumThreads, smem, ctx->stream>>>(ta, tb, p);
   NK_LAUNCHED(ctx, "gemm_tcgen05");
   return NK_OK;
 }
@@ -428,7 +469,7 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
                           "beta == 0 and f32 output");
     p.rs_world = ctx->rs_world;
     p.rs_rows = M / ctx->rs_world;
-    p.m_rot = int(ctx->rs_rank * (p.rs_rows / BLOCK_M));
+    p.m_rot = ctx->rs_rank;
     for (int i = 0; i < ctx->rs_world; ++i) p.rs_dst[i] = ctx->rs_dst[i];
   }
   // K-major: 8-row groups 1024 B apart, +32 B per UMMA_K.  MN-major: 64-wide chunks

@@ -50,13 +50,32 @@ __global__ void peer_barrier_kernel(PeerPtrs flags, int world, int rank, uint32_
 __global__ void __launch_bounds__(1024) reduce_bcast_kernel(const float4* __restrict__ slots, PeerPtrs grads, int world,
                                                             int64_t shard_vec, int64_t offset_vec) {
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < shard_vec; i += stride) {
-    float4 acc = __ldcs(slots + i);
-    for (int s = 1; s < world; ++s) {
-      const float4 v = __ldcs(slots + s * shard_vec + i);
-      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread and slot: few CTAs must still fill the pipes
+  for (int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < shard_vec; i0 += U * stride) {
+    float4 acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      acc[u] = i < shard_vec ? __ldcs(slots + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int r = 0; r < world; ++r) static_cast<float4*>(grads.p[r])[offset_vec + i] = acc;
+    for (int s = 1; s < world; ++s) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        v[u] = i < shard_vec ? __ldcs(slots + s * shard_vec + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u].x += v[u].x, acc[u].y += v[u].y, acc[u].z += v[u].z, acc[u].w += v[u].w;
+    }
+    for (int r = 0; r < world; ++r) {
+      float4* g = static_cast<float4*>(grads.p[r]) + offset_vec;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < shard_vec) g[i] = acc[u];
+      }
+    }
   }
 }
 

@@ -132,7 +132,9 @@ class OverlappedAllReduce:
         self.torch = torch
         self.bucket, self.compute, self.params = bucket, compute_stream, params
         self.comm = torch.cuda.Stream(device=bucket.array.device.index)
-        self.event = torch.cuda.Event()
+        self._events = [torch.cuda.Event() for _ in range(4 * len(params) + 8)]
+        self._ev_i = 0
+        self._pending = []
         self.flat = bucket.as_torch()
         self.ranges = ReadyRanges(min_elems=chunk_elems // 4)
         self.launched = 0
@@ -142,22 +144,36 @@ class OverlappedAllReduce:
             chunks = max(1, min(max_chunks, n // chunk_elems))
             p.set_grad_hook(lambda b, e, off=lay.offsets[pi]: self._ready(off + b, off + e), row_chunks=chunks)
 
-    def _exchange(self, pieces) -> None:
+    # The hook runs INSIDE backward, between two kernel launches of the compute stream: anything slow here (an NCCL
+    # enqueue costs tens of microseconds of host time) delays the next backward kernel.  So the hook only records an
+    # event; the exchange itself is enqueued at the next hook or in wait(), by which time later kernels are queued.
+    def _flush_pending(self) -> None:
         import torch.distributed as dist
+        if not self._pending:
+            return
+        pending, self._pending = self._pending, []
+        for ev, pieces in pending:
+            self.comm.wait_event(ev)
+            with self.torch.cuda.stream(self.comm):
+                for lo, hi in pieces:
+                    dist.all_reduce(self.flat[lo:hi])
+                    self.launched += 1
+
+    def _exchange(self, pieces) -> None:
+        self._flush_pending()
         if not pieces:
             return
-        self.event.record(self.compute)          # everything launched so far (incl. the kernels that wrote the grads)
-        self.comm.wait_event(self.event)
-        with self.torch.cuda.stream(self.comm):
-            for lo, hi in pieces:
-                dist.all_reduce(self.flat[lo:hi])
-                self.launched += 1
+        ev = self._events[self._ev_i % len(self._events)]
+        self._ev_i += 1
+        ev.record(self.compute)           # everything launched so far (incl. the kernels that wrote the grads)
+        self._pending.append((ev, pieces))
 
     def _ready(self, lo: int, hi: int) -> None:
         self._exchange(self.ranges.add(lo, hi))
 
     def wait(self) -> None:
         self._exchange(self.ranges.flush())
+        self._flush_pending()
         self.compute.wait_stream(self.comm)
 
 
@@ -234,11 +250,15 @@ class FusedGradientExchange:
         self.flags = PeerMemory(device, 256, world, rank)
         self.epoch = 0
         self.comm = torch.cuda.Stream(device=device.index)
-        self.event = torch.cuda.Event()
-        self.ranges = ReadyRanges(min_elems=1 << 62)      # everything that is not fused waits for wait()
+        self._events = [torch.cuda.Event() for _ in range(4 * len(shapes) + 8)]
+        self._ev_i = 0
+        self._pending = []
+        self.ranges = ReadyRanges(min_elems=1 << 62)      # everything that is not fused is all-reduced in bulk
         self.flat = self.bucket.as_torch()
         self.pushed = 0
         self.comm_device = None
+        import os
+        self._debug_skip_reduce = bool(os.environ.get("NK_DP_DEBUG_SKIP_REDUCE"))
 
     def attach(self, params) -> None:
         from .device import Device
@@ -261,29 +281,48 @@ class FusedGradientExchange:
                 self.comm_device.ctx)
 
     def _pushed(self, pi: int, pushed: int) -> None:
-        from . import _lib as L
-        import ctypes as C
+        # called inside backward between two kernel launches: record an event only, enqueue the exchange later
+        # (next hook or wait()) so that the host time of the enqueue does not delay the next backward kernel
+        self._flush_pending()
         lay = self.layout
         n = int(np.prod(lay.shapes[pi]))
         if not pushed:                                  # computed locally: plain all-reduce of that range
             self.ranges.held.append((lay.offsets[pi], lay.offsets[pi] + n))
             return
         self.pushed += 1
-        self.event.record(self.compute)                 # the dW GEMM (and its pushes) launched so far
-        self.comm.wait_event(self.event)
-        shard = n // self.world
-        self._barrier()
-        grads = self.bucket_mem.offset_table(lay.offsets[pi] * 4)
-        slots_local = self.slots.local + self.slot_off[pi] * 4
-        L.check(L.lib.nk_reduce_bcast(self.comm_device.ctx, C.c_void_p(slots_local), grads, self.world, self.rank, shard,
-                                      self.reduce_ctas), self.comm_device.ctx)
-        self._barrier()
+        if self._debug_skip_reduce:      # development knob: time the pushing GEMM alone (results are then wrong)
+            return
+        ev = self._events[self._ev_i % len(self._events)]
+        self._ev_i += 1
+        ev.record(self.compute)                         # the dW GEMM (and its pushes) launched so far
+        self._pending.append((ev, pi))
+
+    def _flush_pending(self) -> None:
+        from . import _lib as L
+        import ctypes as C
+        if not self._pending:
+            return
+        pending, self._pending = self._pending, []
+        lay = self.layout
+        for ev, pi in pending:
+            self.comm.wait_event(ev)
+            shard = int(np.prod(lay.shapes[pi])) // self.world
+            self._barrier()                             # every rank's pushes have landed
+            grads = self.bucket_mem.offset_table(lay.offsets[pi] * 4)
+            slots_local = self.slots.local + self.slot_off[pi] * 4
+            L.check(L.lib.nk_reduce_bcast(self.comm_device.ctx, C.c_void_p(slots_local), grads, self.world, self.rank,
+                                          shard, self.reduce_ctas), self.comm_device.ctx)
+            self._barrier()                             # every owner's sums have landed
         self._all_reduce_rest()      # biases etc. that became ready meanwhile ride behind it on the side stream
 
     def _all_reduce_rest(self) -> None:
         import torch.distributed as dist
         rest = self.ranges.flush()
         if rest:
+            ev = self._events[self._ev_i % len(self._events)]
+            self._ev_i += 1
+            ev.record(self.compute)
+            self.comm.wait_event(ev)
             with self.torch.cuda.stream(self.comm):
                 for lo, hi in rest:
                     dist.all_reduce(self.flat[lo:hi])
@@ -293,8 +332,7 @@ class FusedGradientExchange:
         return self.comm_device.launches if self.comm_device is not None else 0
 
     def wait(self) -> None:
+        self._flush_pending()
         if self.ranges.held:
-            self.event.record(self.compute)
-            self.comm.wait_event(self.event)
             self._all_reduce_rest()
         self.compute.wait_stream(self.comm)
