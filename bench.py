@@ -178,7 +178,6 @@ def run_own(args):
     def param(values, grad_view):
         return V.from_ndarray(dev, values, BF).requires_grad(gdt, grad_view)
 
-    host_inputs = []   # (pinned torch tensor, destination CuArray)
 
     def pinned_bf16(arr):
         t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(torch.bfloat16).pin_memory()
@@ -193,28 +192,31 @@ def run_own(args):
         params = [W, b]
         x_host = drng.uniform(-1, 1, (n, fin)).astype(np.float32)
         t_host = drng.uniform(-1, 1, (n, fout)).astype(np.float32)
-        x = V.from_ndarray(dev, x_host, BF).requires_grad()       # input as VarDiff => dX is computed
-        t = V.from_ndarray(dev, t_host, BF)
-        host_inputs = [(pinned_bf16(x_host), x), (pinned_bf16(t_host), t)]
+        px, pt = pinned_bf16(x_host), pinned_bf16(t_host)
+
+        def make_inputs():
+            x = V.from_ndarray(dev, x_host, BF).requires_grad()   # input as VarDiff => dX is computed
+            t = V.from_ndarray(dev, t_host, BF)
+            return {"x": x, "t": t, "copies": [(px, x), (pt, t)]}
         opt = None
         live = {}
 
         # every step builds its graph anew (define-by-run, as a user of the reference does each iteration: the op
         # nodes and their intermediate tensors / gradients are fresh, the leaves persist)
-        def step_resident():            # root = y, backward(seed)
+        def step_resident(inp):         # root = y, backward(seed)
             for p in params:
                 p.zero_grad()
-            x.zero_grad()
-            y = x.mm_t(W) + b
+            inp["x"].zero_grad()
+            y = inp["x"].mm_t(W) + b
             y.forward()
             y.backward(1.0 / (n * fout))
             live["root"] = y
 
-        def step_e2e_compute():         # loss = mse(y, t)
+        def step_e2e_compute(inp):      # loss = mse(y, t)
             for p in params:
                 p.zero_grad()
-            x.zero_grad()
-            loss = (x.mm_t(W) + b).mse_loss(t)
+            inp["x"].zero_grad()
+            loss = (inp["x"].mm_t(W) + b).mse_loss(inp["t"])
             loss.forward()
             loss.backward(1.0)
             live["root"] = loss
@@ -231,22 +233,25 @@ def run_own(args):
             params.append(param(rng.uniform(-k, k, (o,)).astype(np.float32), gviews[2 * li + 1]))
         x_host = drng.uniform(-1, 1, (bsz, sizes[0])).astype(np.float32)
         t_host = np.eye(10, dtype=np.float32)[np.argmax(x_host[:, :10], 1)]
-        x = V.from_ndarray(dev, x_host, BF)
-        t = V.from_ndarray(dev, t_host, BF)
-        host_inputs = [(pinned_bf16(x_host), x), (pinned_bf16(t_host), t)]
+        px, pt = pinned_bf16(x_host), pinned_bf16(t_host)
+
+        def make_inputs():
+            x = V.from_ndarray(dev, x_host, BF)
+            t = V.from_ndarray(dev, t_host, BF)
+            return {"x": x, "t": t, "copies": [(px, x), (pt, t)]}
         opt = nk.optim.StochasticGD.new(0.01, nk.optim.L2(0.0), grad_scale=1.0 / world,
                                         master_weights=args.master_weights)
         for p in params:
             opt.register(p)
         live = {}
 
-        def step_resident():            # a training iteration as written against the reference: new graph every step
+        def step_resident(inp):         # a training iteration as written against the reference: new graph every step
             opt.zero_grad()
-            h = x
+            h = inp["x"]
             for li in range(3):
                 h = h.mm_t(params[2 * li]) + params[2 * li + 1]
                 h = h.relu() if li < 2 else h.softmax(1)
-            loss = h.mse_loss(t)
+            loss = h.mse_loss(inp["t"])
             loss.forward()
             loss.backward(1.0)
             live["root"] = loss
@@ -260,25 +265,28 @@ def run_own(args):
         bc = param(rng.uniform(-k, k, (cout, 1, 1)).astype(np.float32), gb)
         params = [Wc, bc]
         x_host = drng.uniform(0, 1, (n, cin, hh, ww)).astype(np.float32)
-        x = V.from_ndarray(dev, x_host, BF).requires_grad()
-        host_inputs = [(pinned_bf16(x_host), x)]
+        px = pinned_bf16(x_host)
+
+        def make_inputs():
+            x = V.from_ndarray(dev, x_host, BF).requires_grad()
+            return {"x": x, "copies": [(px, x)]}
         opt = None
         live = {}
 
-        def step_resident():
+        def step_resident(inp):
             for p in params:
                 p.zero_grad()
-            x.zero_grad()
-            y = Wc.convolution(x, (1, 1), (1, 1), 1) + bc
+            inp["x"].zero_grad()
+            y = Wc.convolution(inp["x"], (1, 1), (1, 1), 1) + bc
             y.forward()
             y.backward(1.0 / 1e6)
             live["root"] = y
 
-        def step_e2e_compute():
+        def step_e2e_compute(inp):
             for p in params:
                 p.zero_grad()
-            x.zero_grad()
-            loss = (Wc.convolution(x, (1, 1), (1, 1), 1) + bc).mean()
+            inp["x"].zero_grad()
+            loss = (Wc.convolution(inp["x"], (1, 1), (1, 1), 1) + bc).mean()
             loss.forward()
             loss.backward(1.0)
             live["root"] = loss
@@ -303,19 +311,47 @@ def run_own(args):
         compute()
         exchange_and_update()
 
-    loss_pinned = torch.empty((), dtype=torch.float32).pin_memory()
+    # two sets of input leaves: while step k computes on one, the pinned-host -> HBM copy of step k+1 fills the other
+    # on a copy stream (the input pipeline a training loop runs), and the loss of step k is read back one step late
+    sets = [make_inputs(), make_inputs()]
+    copy_stream = torch.cuda.Stream(device=local)
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_pinned = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h2d_views = [[(src, as_torch(var.data_array(), torch, local)) for src, var in st["copies"]] for st in sets]
 
-    def e2e_step():
-        with torch.cuda.stream(stream):
-            for src, var in host_inputs:
-                dst = as_torch(var.data_array(), torch, local)
+    def issue_copy(k):
+        i = k & 1
+        copy_stream.wait_event(consumed[i])          # the step that last read this set has finished with it
+        with torch.cuda.stream(copy_stream):
+            for src, dst in h2d_views[i]:
                 dst.copy_(src.view(dst.shape), non_blocking=True)
-        full_step(step_e2e_compute)
-        loss_t = as_torch(live["root"].data_array(), torch, local)     # this step's loss scalar
-        with torch.cuda.stream(stream):
-            loss_pinned.copy_(loss_t.view(()), non_blocking=True)
-        stream.synchronize()
-        return float(loss_pinned)
+        copied[i].record(copy_stream)
+
+    def e2e_run(steps):
+        """`steps` end-to-end iterations; returns the losses read back (one per step)."""
+        losses = []
+        for i in range(2):
+            consumed[i].record(stream)
+        issue_copy(0)
+        for k in range(steps):
+            i = k & 1
+            if k + 1 < steps:
+                issue_copy(k + 1)
+            stream.wait_event(copied[i])
+            full_step(lambda: step_e2e_compute(sets[i]))
+            loss_t = as_torch(live["root"].data_array(), torch, local)      # this step's loss scalar
+            with torch.cuda.stream(stream):
+                loss_pinned[i].copy_(loss_t.view(()), non_blocking=True)
+            loss_ready[i].record(stream)
+            consumed[i].record(stream)
+            if k >= 1:                                   # read the previous step's loss while this one runs
+                loss_ready[i ^ 1].synchronize()
+                losses.append(float(loss_pinned[i ^ 1]))
+        loss_ready[(steps - 1) & 1].synchronize()
+        losses.append(float(loss_pinned[(steps - 1) & 1]))
+        return losses
 
     def timed(fn, steps, warmup, sample_clocks=False):
         for _ in range(warmup):
@@ -349,7 +385,7 @@ def run_own(args):
         return ms, launches, clocks
 
     W_ = max(args.warmup, 3)
-    ms, launches, clocks = timed(lambda: full_step(step_resident), args.steps, W_, sample_clocks=True)
+    ms, launches, clocks = timed(lambda: full_step(lambda: step_resident(sets[0])), args.steps, W_, sample_clocks=True)
     host_ms = timed.host_ms
     if args.profile:
         if rank == 0:
@@ -360,12 +396,32 @@ def run_own(args):
             dist.destroy_process_group()
         return
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    ms_e2e, _, _ = timed(e2e_step, e2e_steps, 3)
+
+    def timed_e2e(steps):
+        e2e_run(3)                                      # warm-up (pinned buffers, allocator pools)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)                               # every copy of the run is ordered after this point ...
+        losses = e2e_run(steps)
+        e1.record(stream)                               # ... and the last loss read-back before this one
+        e1.synchronize()
+        torch.cuda.synchronize()
+        ms_ = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms_], device=f"cuda:{local}")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_ = float(tt.item())
+        return ms_, losses
+
+    ms_e2e, e2e_losses = timed_e2e(e2e_steps)
 
     flops_step_total = spec["flops_per_rank_step"] * world
     value = flops_step_total / (ms / args.steps * 1e-3) / 1e9
     e2e_value = flops_step_total / (ms_e2e / e2e_steps * 1e-3) / 1e9
-    h2d = sum(int(src.numel()) * 2 for src, _ in host_inputs)
+    h2d = sum(int(src.numel()) * 2 for src, _ in sets[0]["copies"])
 
     out = {
         "metric": METRIC, "value": round(value, 1), "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -380,7 +436,11 @@ def run_own(args):
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_ms, 5), "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e / e2e_steps, 5), "steps": e2e_steps,
-                "what": "pinned host -> HBM copy of the step inputs, forward, backward, loss read back, per step"},
+                "last_loss": round(float(e2e_losses[-1]), 6),
+                "what": "per step: pinned host -> HBM copy of the step's inputs (double-buffered on a copy stream, so the "
+                        "copy of step k+1 overlaps the compute of step k), graph build, forward, backward"
+                        + (", exchange" if world > 1 else "") + (", sgd" if opt is not None else "")
+                        + ", loss scalar read back to pinned host memory (read one step late)"},
     }
 
     # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream
@@ -391,6 +451,16 @@ def run_own(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def measured_traffic(key):
+    """DRAM bytes per launch measured with ncu for the roofline kernels (profiles/r01_traffic.json, committed with the
+    launch lists it was extracted from); None when the file does not have the kernel."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")) as f:
+            return float(json.load(f)[key]["bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def roofline(args, dev, nk, spec, peaks, stream, torch):
@@ -416,7 +486,8 @@ def roofline(args, dev, nk, spec, peaks, stream, torch):
         achieved = 2.0 * n ** 3 / (dur * 1e-3) / 1e12
         peak = peaks["tflops_sustained"]
         return {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-                "frac": round(achieved / peak, 4), "traffic": None,
+                "frac": round(achieved / peak, 4), "traffic": measured_traffic("gemm_tc_4096"),
+                "traffic_note": "tensor-bound kernel: DRAM bytes per launch (ncu, profiles/r01_launches.md) vs 96-128 MB of operands + output",
                 "kernel": "gemm_tc_kernel (tcgen05, 128x256x64 tiles); mean of NT/NN/TN 4096^3 launches",
                 "per_form_ms": {k: round(v, 5) for k, v in forms.items()}, "launches_timed": 3 * iters,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); burst {peaks['tflops_burst']}",
@@ -440,7 +511,7 @@ def roofline(args, dev, nk, spec, peaks, stream, torch):
     bytes_alg = 2.0 * (x.size + y.size)
     achieved = bytes_alg / (dur * 1e-3) / 1e9
     return {"bound": "hbm", "achieved": round(achieved, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": None,
+            "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": measured_traffic("conv_fwd_tc"),
             "kernel": f"conv2d forward ({dev.last_conv_kernel})", "ms": round(dur, 5),
             "algorithmic_bytes_per_launch": bytes_alg, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})"}
 

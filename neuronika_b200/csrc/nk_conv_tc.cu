@@ -1470,13 +1470,18 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       }
     }
   } else if (warp_idx >= kFLoadWarp0 && warp_idx < kFPixelWarp0) {
-    // ===================================================== G loaders: 4-byte cp.async pieces of the (Cout x Wo) row tile
+    // ===================================================== G loaders: cp.async pieces of the (Cout x Wo) row tile.
+    // A G row starts 4-byte aligned in general (2*Wo-byte pitch), but when (pr*Wo) % 4 == 0 -- every other row at
+    // Wo = 222 -- all Cout rows of the tile start 8-byte aligned and 8-byte pieces halve the instruction count.
     const int t = threadIdx.x - kFLoadWarp0 * 32;  // 0..255
-    const int piece = t & 31, o0 = t >> 5;         // rows o0, o0 + 8, ...
+    const int piece = t & 31, o0 = t >> 5;         // 4-byte path: rows o0, o0 + 8, ...
+    const int piece8 = t & 15, o8 = t >> 4;        // 8-byte path: rows o8, o8 + 16, ...
     int stage = 0;
     uint32_t phase = 0;
     const long long plane = (long long)p.ho * p.wo;
     const uint32_t sw = (((piece >> 2) ^ (o0 & 7)) << 4) + (piece & 3) * 4;   // (o0 + 8k) & 7 == o0 & 7
+    const uint32_t sw8 = (((piece8 >> 1) ^ (o8 & 7)) << 4) + (piece8 & 1) * 8;  // (o8 + 16k) & 7 == o8 & 7
+    const bool base8 = ((reinterpret_cast<uintptr_t>(p.g) & 7) == 0) && ((plane & 3) == 0);
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       int n, u0, u1, p_lo, p_hi;
       unit_rows(unit, n, u0, u1, p_lo, p_hi);
@@ -1484,16 +1489,30 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
         const uint32_t sb = base + st_off + stage * stage_bytes;
         const __nv_bfloat16* grow = p.g + (long long)n * p.cout * plane + (long long)pr * p.wo;
+        if (base8 && (((long long)pr * p.wo) & 3) == 0) {
 #pragma unroll
-        for (int c = 0; c < kChunksPerTile; ++c) {
-          int nbytes = (p.wo - c * kChunk - piece * 2) * 2;
-          nbytes = nbytes < 0 ? 0 : (nbytes > 4 ? 4 : nbytes);
-          const __nv_bfloat16* src = grow + (long long)o0 * plane + (nbytes ? c * kChunk + piece * 2 : 0);
-          uint32_t dst = sb + c * chunk_bytes + o0 * 128 + sw;
-          const long long sstep = 8 * plane;
+          for (int c = 0; c < kChunksPerTile; ++c) {
+            int nbytes = (p.wo - c * kChunk - piece8 * 4) * 2;
+            nbytes = nbytes < 0 ? 0 : (nbytes > 8 ? 8 : nbytes);
+            const __nv_bfloat16* src = grow + (long long)o8 * plane + (nbytes ? c * kChunk + piece8 * 4 : 0);
+            uint32_t dst = sb + c * chunk_bytes + o8 * 128 + sw8;
+            const long long sstep = 16 * plane;
+#pragma unroll 4
+            for (int o = o8; o < p.cout; o += 16, src += sstep, dst += 2048)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kChunksPerTile; ++c) {
+            int nbytes = (p.wo - c * kChunk - piece * 2) * 2;
+            nbytes = nbytes < 0 ? 0 : (nbytes > 4 ? 4 : nbytes);
+            const __nv_bfloat16* src = grow + (long long)o0 * plane + (nbytes ? c * kChunk + piece * 2 : 0);
+            uint32_t dst = sb + c * chunk_bytes + o0 * 128 + sw;
+            const long long sstep = 8 * plane;
 #pragma unroll 8
-          for (int o = o0; o < p.cout; o += 8, src += sstep, dst += 1024)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+            for (int o = o0; o < p.cout; o += 8, src += sstep, dst += 1024)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+          }
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ready_bar(stage)) : "memory");
         if (++stage == S) {

@@ -25,8 +25,30 @@ def short(name):
     return name[:70]
 
 
+def traffic_json(tag, workloads):
+    """profiles/<tag>_traffic.json: measured DRAM bytes per launch of the kernels bench.py reports a roofline for."""
+    import json
+    out = {"source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/{tag}_launches.md"}
+    for w in workloads:
+        ks = load(f"gpurun_out/{tag}_launches_{w}.csv")
+        last = ks[-(len(ks) // 5):]
+        if w == "linear":
+            g = [k for k in last if "gemm_tc_kernel" in k["name"]]
+            out["gemm_tc_4096"] = {"bytes_per_launch": sum(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"] for k in g) / max(len(g), 1),
+                                   "launches": len(g)}
+        if w == "conv":
+            for key, pat in (("conv_fwd_tc", "conv_fwd_tc_kernel"), ("conv_bwd_fused_tc", "conv_bwd_fused_kernel")):
+                g = [k for k in last if pat in k["name"]]
+                if g:
+                    out[key] = {"bytes_per_launch": sum(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"] for k in g) / len(g),
+                                "launches": len(g)}
+    with open(f"profiles/{tag}_traffic.json", "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def main():
     tag, workloads = sys.argv[1], sys.argv[2:]
+    traffic_json(tag, workloads)
     steps_captured = 5   # --warmup 3 --steps 2
     print(f"# {tag} -- ncu launch lists of `python bench.py --workload W --profile --steps 2 --warmup 3`\n")
     print("`--clock-control none`; per-launch times are cold-cache and serialised (ncu replays every kernel), so they are\n"
