@@ -1188,9 +1188,10 @@ int nk_conv2d_bwd_input_tc(nk_ctx* ctx, void* dx, const void* g, const void* w, 
 // =====================================================================================================
 namespace {
 
-constexpr int kFThreads = 768;  // warp 0: TMEM reader (dX), 1: MMA + TMEM alloc, 2: TMA (x windows), 3: idle,
-                                // 4..7: shift taps + dW epilogue, 8..15: cp.async G loaders, 16..23: dX pixel warps
-constexpr int kFShiftWarp0 = 4, kFLoadWarp0 = 8, kFPixelWarp0 = 16;
+constexpr int kFThreads = 800;  // warps 0 and 4: TMEM readers (dX; only warps with w % 4 == 0 may read lanes 0..31),
+                                // 1: MMA + TMEM alloc, 2: TMA (x windows), 3: idle, 5..8: shift taps + dW epilogue
+                                // (w % 4 = 1,2,3,0: one per TMEM lane quarter), 9..16: cp.async G loaders, 17..24: dX pixels
+constexpr int kFShiftWarp0 = 5, kFLoadWarp0 = 9, kFPixelWarp0 = 17;
 
 struct ConvBP {
   int n, cin, h, w, cout, ho, wo;
@@ -1262,8 +1263,8 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       ptx::mbar_init(empty_bar(s), 1);
     }
     ptx::mbar_init(d_full_bar, 1);
-    ptx::mbar_init(d_empty_bar, 1);
-    ptx::mbar_init(s_full_bar, 1);
+    ptx::mbar_init(d_empty_bar, 2);   // both readers
+    ptx::mbar_init(s_full_bar, 2);
     ptx::mbar_init(s_empty_bar, 8);
     ptx::mbar_init(done_bar, 1);
     ptx::fence_barrier_init();
@@ -1334,8 +1335,11 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       }
       ptx::mma_commit(done_bar);
     }
-  } else if (warp_idx == 0) {
-    // ===================================================== TMEM reader: dX rows (c,i,j) -> f32 exchange buffer
+  } else if (warp_idx == 0 || warp_idx == 4) {
+    // ===================================================== TMEM readers: dX rows (c,i,j) -> f32 exchange buffer.  D is
+    // single buffered (TMEM also holds the dW accumulators), so the next row's MMAs wait for this drain: two warps
+    // take 128 columns each to halve it (ncu: the kernel was bound by this reader <-> MMA ping-pong, not by issue).
+    const int half = warp_idx >> 2;
     uint32_t rphase = 0, sphase = 0;
     float* srow = reinterpret_cast<float*>(base_ptr + s_off) + (lane < M ? lane : 0) * kSRowFloats;
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
@@ -1346,7 +1350,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         ptx::tc_fence_after();
         ptx::mbar_wait(s_empty_bar, sphase ^ 1u);
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(tmem_base + uint32_t(c0), r);
           ptx::tmem_ld_wait();

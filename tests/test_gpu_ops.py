@@ -585,3 +585,17 @@ def test_conv2d_tensor_core_backward_fused(nk, dev, O, shape, cout):
         del os.environ["NK_CONV_UNFUSED_BWD"]
     assert np.array_equal(dx3.as_ndarray(), dx2.as_ndarray())
     assert np.all(np.abs(dw3.as_ndarray() - dw2.as_ndarray()) <= 1e-4 * sw + 1e-6)
+
+
+@pytest.mark.parametrize("form,M,N,K,cdt,beta,bias,relu", [
+    ("NN", 70, 1027, 10, "bf16", 0.0, False, False),     # dH = G.W of a 10-wide layer: ragged N, scalar tail path
+    ("NN", 8192, 4096, 10, "bf16", 1.0, False, False),   # config 4 at size, accumulating
+    ("NN", 129, 1024, 13, "f32", 0.0, True, True),       # vector path with the bias / ReLU epilogue
+    ("TN", 10, 1027, 515, "f32", 1.0, False, False),     # dW = G^T.H of a 10-wide layer: ragged N and K
+    ("TN", 10, 4096, 8192, "f32", 0.0, False, False),    # config 4 at size
+    ("TN", 12, 512, 4096, "bf16", 0.0, False, False)])
+def test_gemm_skinny_kernels(nk, dev, O, form, M, N, K, cdt, beta, bias, relu):
+    """the two memory-bound kernels behind the 10-wide output layer of config 4 (operands TMA cannot address)"""
+    kern = _bf16_case(nk, dev, O, form, M, N, K, nk.BF16 if cdt == "bf16" else nk.F32, beta=beta, bias=bias, relu=relu,
+                      engine="auto")
+    assert kern == ("simt_small_k" if form == "NN" else "simt_small_m"), kern
