@@ -1177,21 +1177,25 @@ int nk_conv2d_bwd_input_tc(nk_ctx* ctx, void* dx, const void* g, const void* w, 
 // Fused ConvolutionBackward: dW (+ dbias) and dX in ONE pass over the output gradient
 //   (convolution/mod.rs:146-226: the reference's backward() runs both halves back to back, each streaming G)
 //
-// The dW kernel wants the G row tile as the K-major A operand [Cout rows][64 px] x 4 chunks; the dX kernel wants the
-// very same bytes as the MN-major B operand [k = Cout][256 px] (64-px swizzle atoms, leading byte offset = the chunk
-// stride).  So one cp.async pass feeds both UMMA chains:
-//   dX:  D0[(c,i,j)][px]  = sum_o Wt[(c,i,j)][o] * G[o][px]      (TMEM columns [0,256), drained every row)
-//   dW:  Da[co][k]       += sum_px G[co][px] * Xwin[k][px]       (TMEM columns 256.., `nacc` round-robin accumulators,
-//                                                                 kept for all rows the CTA owns)
+// One cp.async pass over G feeds both UMMA chains, because the same swizzled bytes are a valid operand for both:
+//   dW:  Da[co][k]        += sum_px G[co][px] * Xwin[k][px]       A = G chunk read K-major  [Cout rows][64 px]
+//   dX:  Dt[px][(c,i,j)]   = sum_o  G[o][px]  * Wt[(c,i,j)][o]    A = G tile read MN-major  [M = 128 px][K = Cout]
+// The dX product is computed TRANSPOSED -- pixels on the 128 TMEM lanes, the 27 (c,i,j) taps on 32 columns -- so
+// that each of the 256 "pixel" threads reads its own pixel's 27 values with one tcgen05.ld and does the col2im in
+// registers (neighbour pixels v-1, v-2 by warp shuffle, the two pixels across a warp boundary through 256 bytes of
+// shared memory).  The first fused version kept the untransposed D[(c,i,j)][256 px] of the stand-alone dX kernel,
+// needed a reader warp + an f32 exchange buffer, and with the dW accumulators resident could not double-buffer its
+// 256 TMEM columns: reader and UMMAs ping-ponged (profiles/r01_conv_ncu.md).  Transposed, a row tile is 2 x 32
+// columns, double buffered.
 // A CTA owns blocks of dx rows of one image; the kh-1 halo rows of G it recomputes for dX are NOT added to dW (and
 // their x windows are not fetched).  G is read ~1.04x, x ~1x, dx written once.
 // =====================================================================================================
 namespace {
 
-constexpr int kFThreads = 800;  // warps 0 and 4: TMEM readers (dX; only warps with w % 4 == 0 may read lanes 0..31),
-                                // 1: MMA + TMEM alloc, 2: TMA (x windows), 3: idle, 5..8: shift taps + dW epilogue
-                                // (w % 4 = 1,2,3,0: one per TMEM lane quarter), 9..16: cp.async G loaders, 17..24: dX pixels
-constexpr int kFShiftWarp0 = 5, kFLoadWarp0 = 9, kFPixelWarp0 = 17;
+constexpr int kFThreads = 768;  // warp 0: MMA + TMEM alloc, 1: TMA (x windows), 2..3: idle, 4..7: shift taps + dW epilogue,
+                                // 8..15: dX pixel warps (warp 8 + w reads TMEM lane quarter w % 4), 16..23: cp.async G loaders
+constexpr int kFShiftWarp0 = 4, kFPixelWarp0 = 8, kFLoadWarp0 = 16;
+constexpr int kFDxCols = 64;    // TMEM columns of one dX row tile: 2 pixel halves x 32 tap columns
 
 struct ConvBP {
   int n, cin, h, w, cout, ho, wo;
@@ -1209,37 +1213,40 @@ __global__ void __launch_bounds__(kFThreads, 1)
 conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_halo,
                       const ConvBP p) {
   constexpr int KH = 3, KW = 3, M = CIN * KH * KW;
-  static_assert(M <= 32, "the (c,i,j) rows must fit one TMEM lane quarter");
+  static_assert(M <= 32, "the (c,i,j) taps must fit 32 TMEM columns");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw_u32);
-  // layout: [dX weights kblocks x 4 KB (32 rows; the M = 128 UMMA over-reads into stage memory, lanes >= 32 unused)]
-  //         [stages x 4 chunks x (G slot Cout x 128 B | X slots ksteps x 2 KB | halo 1 KB)][S: M rows x 1040 B][barriers]
+  // layout: [dX weights kblocks x 4 KB: B operand, 32 tap rows x 64 output channels, K-major]
+  //         [stages x 4 chunks x (G slot Cout x 128 B | X slots ksteps x 2 KB | halo 1 KB)]
+  //         [boundary exchange: 2 parities x 8 warps x 2 pixels x 32 floats][barriers]
   const uint32_t g_bytes = p.cout * 128;
   const uint32_t x_bytes = p.ksteps * 2048;
   const uint32_t chunk_bytes = g_bytes + x_bytes + 1024;
   const uint32_t stage_bytes = kChunksPerTile * chunk_bytes;
   const uint32_t st_off = p.kblocks * 4096;
-  const uint32_t s_off = st_off + p.stages * stage_bytes;
-  const uint32_t s_bytes = M * kSRowFloats * 4;
-  const uint32_t bar_off = s_off + ((s_bytes + 15u) & ~15u);
+  const uint32_t h_off = st_off + p.stages * stage_bytes;
+  const uint32_t h_bytes = 2 * 8 * 2 * 32 * 4;
+  const uint32_t bar_off = h_off + h_bytes;
   const uint32_t bar_base = base + bar_off;
   const int S = p.stages;
   auto fullx_bar = [&](int s) { return bar_base + 8u * s; };
   auto ready_bar = [&](int s) { return bar_base + 8u * (S + s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
-  const uint32_t d_full_bar = bar_base + 8u * (3 * S), d_empty_bar = d_full_bar + 8, s_full_bar = d_full_bar + 16,
-                 s_empty_bar = d_full_bar + 24, done_bar = d_full_bar + 32, tmem_slot = d_full_bar + 40;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (3 * S) + 40);
+  auto d_full_bar = [&](int d) { return bar_base + 8u * (3 * S + d); };
+  auto d_empty_bar = [&](int d) { return bar_base + 8u * (3 * S + 2 + d); };
+  const uint32_t done_bar = bar_base + 8u * (3 * S + 4), tmem_slot = done_bar + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (3 * S + 5));
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   {
     uint4* z = reinterpret_cast<uint4*>(base_ptr);
-    for (uint32_t i = threadIdx.x; i < s_off / 16; i += kFThreads) z[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = threadIdx.x; i < bar_off / 16; i += kFThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
-  // dX A operand: A[m][o] = W[o][c][i][j], m = (c*KH + i)*KW + j ; K-major SWIZZLE_128B, 64 output channels per block
+  // dX B operand: B[m][o] = W[o][c][i][j], m = (c*KH + i)*KW + j ; K-major SWIZZLE_128B, 64 output channels per block
+  // (N = 32 rows; rows >= M stay zero)
   for (int idx = threadIdx.x; idx < p.cout * M; idx += kFThreads) {
     const int o = idx / M, m = idx - o * M;
     const int blk = o >> 6, col = o & 63;
@@ -1254,7 +1261,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           0x3F803F80u;
     }
   }
-  if (warp_idx == 0 && lane == 0) {
+  if (warp_idx == 1 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_halo);
     for (int s = 0; s < S; ++s) {
@@ -1262,14 +1269,14 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       ptx::mbar_init(ready_bar(s), 256 + 4);
       ptx::mbar_init(empty_bar(s), 1);
     }
-    ptx::mbar_init(d_full_bar, 1);
-    ptx::mbar_init(d_empty_bar, 2);   // both readers
-    ptx::mbar_init(s_full_bar, 2);
-    ptx::mbar_init(s_empty_bar, 8);
+    for (int d = 0; d < 2; ++d) {
+      ptx::mbar_init(d_full_bar(d), 1);
+      ptx::mbar_init(d_empty_bar(d), 8);   // the 8 pixel warps
+    }
     ptx::mbar_init(done_bar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp_idx == 1) {
+  if (warp_idx == 0) {
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
@@ -1278,7 +1285,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tmem_dw = tmem_base + 256u;
+  const uint32_t tmem_dw = tmem_base + 2u * kFDxCols;   // dW accumulators behind the two dX buffers
 
   // every role walks the same sequence of (unit, G row) tiles; G row pr feeds dW only when the unit owns it (pr >= u0)
   auto unit_rows = [&](int unit, int& n, int& u0, int& u1, int& p_lo, int& p_hi) {
@@ -1291,11 +1298,11 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   };
   bool any_owned = false;
 
-  if (warp_idx == 1) {
+  if (warp_idx == 0) {
     if (lane == 0) {  // ===================================================== MMA issuer
-      const uint32_t idesc_dx = ptx::make_idesc_bf16(128, 256, false, true);
+      const uint32_t idesc_dx = ptx::make_idesc_bf16(128, 32, true, false);
       const uint32_t idesc_dw = ptx::make_idesc_bf16(128, p.ncols, false, false);
-      int stage = 0;
+      int stage = 0, db = 0;
       uint32_t phase = 0, dphase = 0, started = 0, cnt = 0;
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
         int n, u0, u1, p_lo, p_hi;
@@ -1303,16 +1310,22 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         for (int pr = p_lo; pr <= p_hi; ++pr) {
           ptx::mbar_wait(ready_bar(stage), phase);
           ptx::fence_proxy_async();  // cp.async / st.shared (generic proxy) writes -> async proxy (UMMA)
-          ptx::mbar_wait(d_empty_bar, dphase ^ 1u);
+          ptx::mbar_wait(d_empty_bar(db), dphase ^ 1u);
           ptx::tc_fence_after();
           const uint32_t sb = base + st_off + stage * stage_bytes;
-          for (int ks = 0; ks < p.cout / 16; ++ks) {
-            const uint64_t adesc = ptx::make_smem_desc_sw128(base + (ks >> 2) * 4096 + (ks & 3) * 32, 16, 1024);
-            const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + ks * 2048, chunk_bytes, 1024);
-            ptx::mma_f16_ss(tmem_base, adesc, bdesc, idesc_dx, ks != 0 ? 1u : 0u);
+          // dX (transposed): pixel half hf = chunks 2hf, 2hf+1 as the MN-major A operand (64-px atoms chunk_bytes apart)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const uint32_t tmem_d = tmem_base + uint32_t(db * kFDxCols + hf * 32);
+            for (int ks = 0; ks < p.cout / 16; ++ks) {
+              const uint64_t adesc = ptx::make_smem_desc_sw128(sb + 2 * hf * chunk_bytes + ks * 2048, chunk_bytes, 1024);
+              const uint64_t bdesc = ptx::make_smem_desc_sw128(base + (ks >> 2) * 4096 + (ks & 3) * 32, 16, 1024);
+              ptx::mma_f16_ss(tmem_d, adesc, bdesc, idesc_dx, ks != 0 ? 1u : 0u);
+            }
           }
-          ptx::mma_commit(d_full_bar);
-          dphase ^= 1u;
+          ptx::mma_commit(d_full_bar(db));
+          db ^= 1;
+          if (db == 0) dphase ^= 1u;
           if (pr >= u0) {
             for (int c = 0; c < p.cpr; ++c) {
               const uint64_t adesc = ptx::make_smem_desc_sw128(sb + c * chunk_bytes, 16, 1024);
@@ -1335,42 +1348,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       }
       ptx::mma_commit(done_bar);
     }
-  } else if (warp_idx == 0 || warp_idx == 4) {
-    // ===================================================== TMEM readers: dX rows (c,i,j) -> f32 exchange buffer.  D is
-    // single buffered (TMEM also holds the dW accumulators), so the next row's MMAs wait for this drain: two warps
-    // take 128 columns each to halve it (ncu: the kernel was bound by this reader <-> MMA ping-pong, not by issue).
-    const int half = warp_idx >> 2;
-    uint32_t rphase = 0, sphase = 0;
-    float* srow = reinterpret_cast<float*>(base_ptr + s_off) + (lane < M ? lane : 0) * kSRowFloats;
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
-      int n, u0, u1, p_lo, p_hi;
-      unit_rows(unit, n, u0, u1, p_lo, p_hi);
-      for (int pr = p_lo; pr <= p_hi; ++pr) {
-        ptx::mbar_wait(d_full_bar, rphase);
-        ptx::tc_fence_after();
-        ptx::mbar_wait(s_empty_bar, sphase ^ 1u);
-#pragma unroll 1
-        for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(tmem_base + uint32_t(c0), r);
-          ptx::tmem_ld_wait();
-          if (lane < M) {
-#pragma unroll
-            for (int v = 0; v < 8; ++v)
-              *reinterpret_cast<uint4*>(srow + c0 + v * 4) = make_uint4(r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);
-          }
-        }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::mbar_arrive(d_empty_bar);
-          ptx::mbar_arrive(s_full_bar);
-        }
-        rphase ^= 1u;
-        sphase ^= 1u;
-      }
-    }
-  } else if (warp_idx == 2) {
+  } else if (warp_idx == 1) {
     if (lane == 0) {  // ===================================================== TMA: tap-0 x windows + halos of owned rows
       int stage = 0;
       uint32_t phase = 0;
@@ -1400,7 +1378,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
       }
     }
-  } else if (warp_idx >= kFShiftWarp0 && warp_idx < kFLoadWarp0) {
+  } else if (warp_idx >= kFShiftWarp0 && warp_idx < kFPixelWarp0) {
     // ===================================================== shift warps: taps j = 1, 2 of the x windows (two K-rows per
     // instruction, see shift_taps_kw3), then the dW epilogue
     const int wrp = warp_idx - kFShiftWarp0;
@@ -1414,7 +1392,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       for (int pr = p_lo; pr <= p_hi; ++pr) {
         ptx::mbar_wait_relaxed(fullx_bar(stage), phase);
         if (pr >= u0) {
-          any_owned = true;  // at least one dW chain ran: every accumulator has been written (16 UMMAs >= nacc)
+          any_owned = true;  // at least one dW chain ran: every accumulator has been written (>= 4 UMMAs >= nacc)
           uint8_t* sp = base_ptr + st_off + stage * stage_bytes;
           for (int c = 0; c < p.cpr; ++c) {
             uint8_t* xs = sp + c * chunk_bytes + g_bytes;
@@ -1473,7 +1451,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
       }
     }
-  } else if (warp_idx >= kFLoadWarp0 && warp_idx < kFPixelWarp0) {
+  } else if (warp_idx >= kFLoadWarp0) {
     // ===================================================== G loaders: cp.async pieces of the (Cout x Wo) row tile.
     // A G row starts 4-byte aligned in general (2*Wo-byte pitch), but when (pr*Wo) % 4 == 0 -- every other row at
     // Wo = 222 -- all Cout rows of the tile start 8-byte aligned and 8-byte pieces halve the instruction count.
@@ -1525,13 +1503,17 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
       }
     }
-  } else if (warp_idx >= kFPixelWarp0) {
-    // ===================================================== pixel warps: col2im in registers, one dx column each
-    const int v = threadIdx.x - kFPixelWarp0 * 32;  // 0..255
+  } else if (warp_idx >= kFPixelWarp0 && warp_idx < kFLoadWarp0) {
+    // ===================================================== pixel warps: thread = dx column v = TMEM lane of half v / 128.
+    // One tcgen05.ld brings this pixel's 27 tap products; dx[c][p+i][v] += sum_j Dt[v-j][(c,i,j)]: the j = 1, 2 terms
+    // come from lanes v-1, v-2 (shuffle), across a warp boundary from the previous warp's lanes 30, 31 (shared memory)
+    const int pw = warp_idx - kFPixelWarp0;          // 0..7 ; (warp_idx & 3) == (pw & 3): the TMEM lane quarter
+    const int v = pw * 32 + lane;
     const bool col_live = v < p.w;
-    uint32_t sphase = 0;
+    int db = 0;
+    uint32_t dphase = 0, parity = 0;
     const long long img = (long long)p.h * p.w;
-    const float* Sb = reinterpret_cast<const float*>(base_ptr + s_off);
+    float* Hx = reinterpret_cast<float*>(base_ptr + h_off);
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
       int n, u0, u1, p_lo, p_hi;
       unit_rows(unit, n, u0, u1, p_lo, p_hi);
@@ -1559,22 +1541,40 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
       };
       for (int pr = p_lo; pr <= p_hi; ++pr) {
-        ptx::mbar_wait_relaxed(s_full_bar, sphase);
+        ptx::mbar_wait_relaxed(d_full_bar(db), dphase);
+        ptx::tc_fence_after();
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t((pw & 3) * 32) << 16) + uint32_t(db * kFDxCols + (pw >> 2) * 32), r);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(d_empty_bar(db));
+        db ^= 1;
+        if (db == 0) dphase ^= 1u;
+        // publish the two last pixels of this warp for the next warp's lanes 0 and 1
+        float* mine = Hx + (parity * 8 + pw) * 64;
+        if (lane >= 30) {
+#pragma unroll
+          for (int m = 0; m < M; ++m) mine[(lane - 30) * 32 + m] = __uint_as_float(r[m]);
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float* prev = Hx + (parity * 8 + (pw > 0 ? pw - 1 : 0)) * 64;   // [0]: pixel 32pw-2, [1]: pixel 32pw-1
+        parity ^= 1u;
 #pragma unroll
         for (int c = 0; c < CIN; ++c)
 #pragma unroll
           for (int i = 0; i < KH; ++i) {
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < KW; ++j) {
-              const int q = v - j;
-              if (q >= 0) acc += Sb[((c * KH + i) * KW + j) * kSRowFloats + q];
-            }
+            const int m0 = (c * KH + i) * KW;
+            const float a0 = __uint_as_float(r[m0]);
+            float a1 = __shfl_up_sync(0xffffffffu, __uint_as_float(r[m0 + 1]), 1);
+            float a2 = __shfl_up_sync(0xffffffffu, __uint_as_float(r[m0 + 2]), 2);
+            if (lane == 0) a1 = pw > 0 ? prev[32 + m0 + 1] : 0.f;
+            if (lane < 2) a2 = pw > 0 ? prev[lane * 32 + m0 + 2] : 0.f;
+            float acc = a0;       // same order as the stand-alone kernel: j = 0, 1, 2
+            acc += a1;
+            acc += a2;
             ring[c][i] += acc;
           }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(s_empty_bar);
-        sphase ^= 1u;
         emit(pr);
       }
       for (int u = p_hi + 1; u < u1; ++u) emit(u);  // rows below the last G row (last block of an image)
@@ -1583,7 +1583,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp_idx == 1) {
+  if (warp_idx == 0) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
@@ -1623,13 +1623,14 @@ int nk_conv2d_bwd_fused_tc(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int 
   p.ksteps = 3 * p.ng;
   p.ncols = p.ksteps * 16;
   p.fuse_dbias = (dbias != nullptr && p.R < 16) ? 1 : 0;
-  p.nacc = 1;
-  while (p.nacc * 2 * p.ncols <= 256 && p.nacc < 16) p.nacc *= 2;
+  p.nacc = 1;   // round-robin dW accumulators in the 384 TMEM columns behind the two 64-column dX buffers
+  while (p.nacc * 2 * p.ncols <= 384 && p.nacc < 16) p.nacc *= 2;
   p.cpr = (p.wo + kChunk - 1) / kChunk;
+  while (p.nacc > p.cpr * 4) p.nacc /= 2;   // one owned row (4 UMMAs per live chunk) must touch every accumulator
   p.kblocks = (p.cout + 63) / 64;
   const size_t stage_bytes = size_t(kChunksPerTile) * (p.cout * 128 + p.ksteps * 2048 + 1024);
-  const size_t s_bytes = (size_t(p.cin) * 9 * kSRowFloats * 4 + 15) & ~size_t(15);
-  const size_t fixed = 1024 + size_t(p.kblocks) * 4096 + s_bytes + 512;
+  const size_t h_bytes = 2 * 8 * 2 * 32 * 4;   // boundary exchange of the pixel warps
+  const size_t fixed = 1024 + size_t(p.kblocks) * 4096 + h_bytes + 512;
   if (fixed + 2 * stage_bytes > 232448) return NK_ERR_UNSUPPORTED;
   p.stages = int((232448 - fixed) / stage_bytes);
   if (p.stages > 4) p.stages = 4;
