@@ -798,7 +798,10 @@ int nk_conv2d_bwd_kernel_tc(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, c
   p.ncols = p.ksteps * 16;
   if (p.ncols > 256 || p.ng > 4) return NK_ERR_UNSUPPORTED;
   p.fuse_dbias = (dbias != nullptr && p.kh * p.cpg < 16) ? 1 : 0;
-  p.nacc = p.ncols <= 32 ? 16 : p.ncols <= 64 ? 8 : p.ncols <= 128 ? 4 : 2;
+  // ONE accumulator: tools/umma_probe.cu (profiles/r01_umma_issue_probe.txt) measures 77 cycles per UMMA when consecutive
+  // instructions accumulate into the same TMEM columns and 219 when they alternate between accumulators -- the
+  // round-robin scheme tried first made every instruction pay the switch
+  p.nacc = 1;
   p.tmem_cols = 512;
   p.cpr = (p.wo + kChunk - 1) / kChunk;
   p.chunks_per_img = p.ho * p.cpr;
@@ -1623,8 +1626,9 @@ int nk_conv2d_bwd_fused_tc(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int 
   p.ksteps = 3 * p.ng;
   p.ncols = p.ksteps * 16;
   p.fuse_dbias = (dbias != nullptr && p.R < 16) ? 1 : 0;
-  p.nacc = 1;   // round-robin dW accumulators in the 384 TMEM columns behind the two 64-column dX buffers
-  while (p.nacc * 2 * p.ncols <= 384 && p.nacc < 16) p.nacc *= 2;
+  // ONE dW accumulator: consecutive UMMAs into the same TMEM columns issue every 77 cycles, alternating accumulators
+  // costs 219 cycles per instruction (tools/umma_probe.cu, profiles/r01_umma_issue_probe.txt)
+  p.nacc = 1;
   p.cpr = (p.wo + kChunk - 1) / kChunk;
   while (p.nacc > p.cpr * 4) p.nacc /= 2;   // one owned row (4 UMMAs per live chunk) must touch every accumulator
   p.kblocks = (p.cout + 63) / 64;
