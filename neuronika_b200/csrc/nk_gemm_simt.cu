@@ -364,9 +364,10 @@ int launch_skinny(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int
     if (rc) return rc;
     NK_CUDA(ctx, cudaMemsetAsync(scratch, 0, size_t(M) * size_t(N) * sizeof(float), ctx->stream));
     const int64_t gx = (N + 511) / 512;
-    // about two blocks per SM: every block ends with M*512 atomics into the same M x N scratch, so many short blocks
-    // (the first version used 64-deep slabs: 8.4 M contended atomics, 91 us at 10 x 4096 x 8192) lose to few long ones
-    int64_t gy = (2 * int64_t(ctx->sm_count) + gx - 1) / gx;
+    // ~8 blocks of 128 threads per SM: the kernel is bound by the latency of the streamed operand, so it wants many
+    // threads with loads in flight (measured at 10 x 4096 x 8192: 1024 blocks 91 us, 256 blocks 150 us; the M*512
+    // atomics each block ends with are not what limits it)
+    int64_t gy = (2 * int64_t(ctx->sm_count) * 4 + gx - 1) / gx;
     int64_t k_per_block = (K + gy - 1) / gy;
     k_per_block = (k_per_block + 63) / 64 * 64;
     gy = (K + k_per_block - 1) / k_per_block;
