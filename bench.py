@@ -163,15 +163,23 @@ def run_own(args):
     if gdt != nk.F32 and exchange_kind == "fused":
         exchange_kind = "nccl"       # the fused reduce-scatter epilogue sums f32 gradients
     fused_exchange = []
+    exchange_state = {"kind": exchange_kind}
 
     def make_bucket(shapes):
         if world == 1:      # no exchange step: let the graph own (and lazily clear) the gradients
             return None, [None] * len(shapes)
         if exchange_kind == "fused":
-            ex = FusedGradientExchange(dev, stream, shapes, world, rank,
-                                       reduce_ctas=int(os.environ.get("NK_DP_REDUCE_CTAS", "20")))
-            fused_exchange.append(ex)
-            return ex.bucket, ex.bucket.views
+            try:
+                ex = FusedGradientExchange(dev, stream, shapes, world, rank,
+                                           reduce_ctas=int(os.environ.get("NK_DP_REDUCE_CTAS", "20")))
+                fused_exchange.append(ex)
+                return ex.bucket, ex.bucket.views
+            except RuntimeError as e:
+                # peer memory could not be set up (the error is collective: every rank gets here together): the
+                # exchange falls back from the fused NVLink path to NCCL all-reduce, and the JSON line says so
+                if rank == 0:
+                    print(f"bench: fused exchange unavailable ({e}); using the NCCL all-reduce exchange", file=sys.stderr)
+                exchange_state["kind"] = "nccl"
         b = GradientBucket(dev, shapes, gdt)
         return b, b.views
 
@@ -428,8 +436,8 @@ def run_own(args):
         "warmup": W_, "ms_per_step": round(ms / args.steps, 5), "higher_is_better": True,
         "scaling": spec["scaling"], "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "samples_per_s": round(spec["samples_per_rank_step"] * world / (ms / args.steps * 1e-3), 1),
-        "config": {"workload": spec["name"], "grad_dtype": args.grad_dtype, "parallelism": f"dp{world}", "exchange": exchange_kind,
-                   "step": "zero_grad -> forward -> backward" + ({"none": "", "nccl": " (+ overlapped nccl all_reduce of each layer's grad slice)", "fused": " (dW GEMM epilogue reduce-scatters over NVLink peer memory, owner reduce + broadcast on a side stream; nccl for the small tensors)"}[exchange_kind])
+        "config": {"workload": spec["name"], "grad_dtype": args.grad_dtype, "parallelism": f"dp{world}", "exchange": exchange_state["kind"],
+                   "step": "zero_grad -> forward -> backward" + ({"none": "", "nccl": " (+ overlapped nccl all_reduce of each layer's grad slice)", "fused": " (dW GEMM epilogue reduce-scatters over NVLink peer memory, owner reduce + broadcast on a side stream; nccl for the small tensors)"}[exchange_state["kind"]])
                            + (" -> sgd" if opt is not None else ""),
                    "l2": "working set per step exceeds the 126 MB L2 (no flush needed)",
                    "kernels": {"gemm": dev.last_gemm_kernel, "conv": dev.last_conv_kernel}},

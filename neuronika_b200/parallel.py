@@ -186,22 +186,56 @@ class PeerMemory:
         import torch.distributed as dist
         from . import _lib as L
         self.device, self.world, self.rank, self.nbytes = device, world, rank, int(nbytes)
-        p = C.c_void_p()
-        L.check(L.lib.nk_ipc_alloc(device.ctx, self.nbytes, C.byref(p)), device.ctx)
-        self.local = int(p.value)
-        h = C.create_string_buffer(64)
-        L.check(L.lib.nk_ipc_export(device.ctx, C.c_void_p(self.local), h), device.ctx)
+        # every step below is followed by a collective agreement, so that a failure on one rank (no peer access, IPC
+        # disabled in the container, out of memory) raises on ALL ranks instead of leaving the others in a collective
+        self.local, handle, err = 0, None, None
+        try:
+            p = C.c_void_p()
+            L.check(L.lib.nk_ipc_alloc(device.ctx, self.nbytes, C.byref(p)), device.ctx)
+            self.local = int(p.value)
+            h = C.create_string_buffer(64)
+            L.check(L.lib.nk_ipc_export(device.ctx, C.c_void_p(self.local), h), device.ctx)
+            handle = bytes(h.raw)
+        except Exception as e:      # noqa: BLE001 -- reported below, on every rank
+            err = repr(e)
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(h.raw))
+        dist.all_gather_object(handles, (handle, err))
+        bad = [(r, e) for r, (hd, e) in enumerate(handles) if hd is None]
+        if bad:
+            self._release()
+            raise RuntimeError(f"peer memory: allocation / export failed on rank(s) {bad}")
         self.ptrs: List[int] = []
-        for r in range(world):
-            if r == rank:
-                self.ptrs.append(self.local)
-            else:
-                q = C.c_void_p()
-                L.check(L.lib.nk_ipc_open(device.ctx, C.create_string_buffer(handles[r], 64), C.byref(q)), device.ctx)
-                self.ptrs.append(int(q.value))
+        self._opened: List[int] = []
+        err = None
+        try:
+            for r in range(world):
+                if r == rank:
+                    self.ptrs.append(self.local)
+                else:
+                    q = C.c_void_p()
+                    L.check(L.lib.nk_ipc_open(device.ctx, C.create_string_buffer(handles[r][0], 64), C.byref(q)),
+                            device.ctx)
+                    self.ptrs.append(int(q.value))
+                    self._opened.append(int(q.value))
+        except Exception as e:      # noqa: BLE001
+            err = repr(e)
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        bad = [(r, e) for r, e in enumerate(errs) if e is not None]
+        if bad:
+            self._release()
+            raise RuntimeError(f"peer memory: opening the peers' handles failed on rank(s) {bad}")
         self.table = (C.c_void_p * world)(*self.ptrs)
+
+    def _release(self) -> None:
+        import ctypes as C
+        from . import _lib as L
+        for q in getattr(self, "_opened", []):
+            L.lib.nk_ipc_close(self.device.ctx, C.c_void_p(q))
+        self._opened = []
+        if self.local:
+            L.lib.nk_ipc_free(self.device.ctx, C.c_void_p(self.local))
+            self.local = 0
 
     def offset_table(self, byte_offset: int):
         import ctypes as C

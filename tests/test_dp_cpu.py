@@ -137,3 +137,97 @@ def test_fused_exchange_eligibility():
     assert not rs_eligible((4096,), 2) and not rs_eligible((10, 4096), 2) and not rs_eligible((64, 3, 3, 3), 2)
     assert not rs_eligible((4096, 4096), 1) and not rs_eligible((384, 4096), 2)      # 192 rows per rank: not whole tiles
     assert not rs_eligible((256, 256), 2)                                             # too small to matter
+
+
+class _FakePeerLib:
+    """Stand-in for the nk_ipc_* entry points (no GPU): 'allocates' fake addresses and hands out 64-byte handles that
+    encode them, so the collective control flow of parallel.PeerMemory can run under gloo."""
+
+    def __init__(self, rank, fail_alloc_on=None, fail_open_on=None):
+        self.rank, self.fail_alloc_on, self.fail_open_on = rank, fail_alloc_on, fail_open_on
+        self.freed, self.closed = [], []
+
+    def nk_ipc_alloc(self, ctx, nbytes, out):
+        if self.rank == self.fail_alloc_on:
+            return -3
+        out._obj.value = 0x10000000 * (self.rank + 1)
+        return 0
+
+    def nk_ipc_export(self, ctx, ptr, handle):
+        handle.raw = int(ptr.value).to_bytes(8, "little") + bytes(56)
+        return 0
+
+    def nk_ipc_open(self, ctx, handle, out):
+        if self.rank == self.fail_open_on:
+            return -2
+        out._obj.value = int.from_bytes(handle.raw[:8], "little") + 0x1000      # a different (mapped) address
+        return 0
+
+    def nk_ipc_close(self, ctx, ptr):
+        self.closed.append(int(ptr.value))
+        return 0
+
+    def nk_ipc_free(self, ctx, ptr):
+        self.freed.append(int(ptr.value))
+        return 0
+
+
+def _peer_worker(rank, world, port, q, fail_alloc_on, fail_open_on):
+    import torch.distributed as dist
+
+    from neuronika_b200 import _lib as L
+    from neuronika_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fake = _FakePeerLib(rank, fail_alloc_on, fail_open_on)
+    real_lib, real_check = L.lib, L.check
+    L.lib = fake
+
+    def check(rc, ctx=None):
+        if rc != 0:
+            raise L.NkError(rc, "fake failure")
+    L.check = check
+
+    class Dev:
+        ctx = None
+    try:
+        m = parallel.PeerMemory(Dev(), 1024, world, rank)
+        out = ("ok", m.ptrs, [int(v) for v in m.offset_table(16)])
+    except RuntimeError as e:
+        out = ("raised", str(e), (list(fake.freed), list(fake.closed)))
+    finally:
+        L.lib, L.check = real_lib, real_check
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_alloc_on,fail_open_on", [(None, None), (1, None), (None, 0)])
+def test_peer_memory_setup_is_collective(fail_alloc_on, fail_open_on):
+    """parallel.PeerMemory (the buffers of the fused NVLink exchange): every rank ends up with the same view of who
+    owns which address, and a failure on ONE rank raises on ALL ranks (nobody is left waiting in a collective), after
+    releasing what was mapped -- that is what lets bench.py fall back to the NCCL exchange consistently."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q, fail_alloc_on, fail_open_on)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if fail_alloc_on is None and fail_open_on is None:
+        for r in (0, 1):
+            kind, ptrs, off = res[r]
+            assert kind == "ok"
+            assert ptrs[r] == 0x10000000 * (r + 1)                          # own allocation
+            assert ptrs[1 - r] == 0x10000000 * (2 - r) + 0x1000             # the peer's buffer, as mapped here
+            assert off == [p + 16 for p in ptrs]
+    else:
+        assert res[0][0] == "raised" and res[1][0] == "raised"
+        for r in (0, 1):
+            freed, closed = res[r][2]
+            if r != fail_alloc_on:
+                assert freed == [0x10000000 * (r + 1)]                      # local buffer released on the way out
