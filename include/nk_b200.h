@@ -127,12 +127,66 @@ int nk_log_softmax_bwd(nk_ctx* ctx, void* dx, const void* y, const void* g, int6
 int nk_mse_fwd(nk_ctx* ctx, float* loss, const void* x, const void* t, size_t n, int dtype, int mean);
 int nk_mse_bwd(nk_ctx* ctx, void* dx, const void* x, const void* t, const float* g, size_t n,
                int dtype, int mean, float beta);
-int nk_nll_fwd(nk_ctx* ctx, float* loss, const void* logp, const void* target, int64_t n,
-               int64_t c, int dtype, int mean);
-int nk_nll_bwd(nk_ctx* ctx, void* dlogp, const void* target, const float* g, int64_t n, int64_t c,
-               int dtype, int mean, float beta);
+/* NLL: `target` holds the class ids as floats (`target as usize`, nll/mod.rs:55) in element type
+ * target_dtype -- NK_F32 whatever the input's type, or NK_BF16 (exact only for ids <= 256, so
+ * rejected when c > 256). */
+int nk_nll_fwd(nk_ctx* ctx, float* loss, const void* logp, const void* target, int target_dtype,
+               int64_t n, int64_t c, int dtype, int mean);
+int nk_nll_bwd(nk_ctx* ctx, void* dlogp, const void* target, int target_dtype, const float* g,
+               int64_t n, int64_t c, int dtype, int mean, float beta);
 int nk_sum_fwd(nk_ctx* ctx, float* out, const void* x, size_t n, int dtype, int mean);
 int nk_sum_bwd(nk_ctx* ctx, void* dx, const float* g, size_t n, int dtype, int mean, float beta);
+
+/* ---- the rest of the elementwise family (csrc/nk_pointwise.cu) ----
+ * binary ops broadcast like nk_add_bcast_fwd (utils.rs:97-125):
+ *   subtraction/mod.rs:44-49, multiplication/mod.rs:44-49, division/mod.rs:44-49.
+ * nk_binary_bcast_bwd accumulates ONE operand's gradient (side 0 = left, 1 = right):
+ *   dst = beta*dst + unbroadcast(factor(g, l, r) -> shape of that operand), factor =
+ *   SUB: g | -g (subtraction/mod.rs:87-92,130-135); MUL: g*r | g*l (multiplication/mod.rs:90-148);
+ *   DIV: g/r | -g*l/r^2 (division/mod.rs:90-151).  l / r may be NULL where the factor ignores them. */
+typedef enum { NK_BIN_ADD = 0, NK_BIN_SUB = 1, NK_BIN_MUL = 2, NK_BIN_DIV = 3 } nk_binary_op;
+int nk_binary_bcast_fwd(nk_ctx* ctx, int op, void* y, const void* l, const void* r, int dtype,
+                        int y_ndim, const int64_t* y_shape, int l_ndim, const int64_t* l_shape,
+                        int r_ndim, const int64_t* r_shape);
+int nk_binary_bcast_bwd(nk_ctx* ctx, int op, int side, void* dst, int dst_dtype, const void* g,
+                        const void* l, const void* r, int dtype, int l_ndim, const int64_t* l_shape,
+                        int r_ndim, const int64_t* r_shape, float beta);
+/* unary ops: y = f(x); dx = beta*dx + g * f'(saved), where `saved` is the tensor the reference's
+ * Backward node keeps -- the OUTPUT y for EXP, SQRT, SIGMOID, TANH; the INPUT x for LN, SOFTPLUS,
+ * LEAKY_RELU (slope 0.01), POWI; ignored for NEG.  iparam = the integer exponent of POWI
+ * (negation/mod.rs:32-68, exp/mod.rs:32-74, logn/mod.rs:32-74, sqrt/mod.rs:32-74, sigmoid/mod.rs:32-76,
+ * tanh/mod.rs:32-76, softplus/mod.rs:32-76, leaky_relu/mod.rs:33-81, power/mod.rs:41-88). */
+typedef enum { NK_UN_NEG = 0, NK_UN_EXP = 1, NK_UN_LN = 2, NK_UN_SQRT = 3, NK_UN_SIGMOID = 4,
+               NK_UN_TANH = 5, NK_UN_SOFTPLUS = 6, NK_UN_LEAKY_RELU = 7, NK_UN_POWI = 8 } nk_unary_op;
+int nk_unary_fwd(nk_ctx* ctx, int op, void* y, const void* x, size_t n, int dtype, int iparam);
+int nk_unary_bwd(nk_ctx* ctx, int op, void* dx, const void* saved, const void* g, size_t n, int dtype,
+                 int iparam, float beta);
+/* dst (reversed shape) = beta*dst + src^T : ndarray's `.t()` reverses every axis
+ * (transpose/mod.rs:32-36 forward with beta = 0; :66-68 backward `dX += G^T` with beta = 1). Bit exact. */
+int nk_transpose(nk_ctx* ctx, void* dst, int dst_dtype, const void* src, int src_dtype, int ndim,
+                 const int64_t* src_shape, float beta);
+/* padding of the last nsp (1..3) dims of (planes, s...) with a mode; backward is the interior slice
+ * for every mode, as in the reference (pad/mod.rs:157-182). */
+typedef enum { NK_PAD_CONSTANT = 0, NK_PAD_REFLECTIVE = 1, NK_PAD_REPLICATIVE = 2 } nk_pad_mode;
+int nk_padnd_fwd(nk_ctx* ctx, void* y, const void* x, int64_t planes, int nsp, const int64_t* in_sp,
+                 const int64_t* pad, int mode, float value, int dtype);
+int nk_padnd_bwd(nk_ctx* ctx, void* dx, const void* g, int64_t planes, int nsp, const int64_t* in_sp,
+                 const int64_t* pad, int dtype, float beta);
+
+/* ---- matrix-vector / vector-matrix / vector-vector products (8-f rank 3; csrc/nk_gemv.cu) ----
+ * A is (rows, cols) row-major.  trans = 0: y[rows] = beta*y + A.x[cols] (MatrixVectorMul::forward,
+ * matrix_vector_mul/mod.rs:32-40; vm dv, vector_matrix_mul/mod.rs:64-72); trans = 1: y[cols] = beta*y +
+ * A^T.x[rows] (VectorMatrixMul::forward :32-40; mv dv, matrix_vector_mul/mod.rs:93-101).
+ * nk_outer_acc: A = beta*A + u (x) v (mv dA :64-69, vm dA vector_matrix_mul/mod.rs:96-101).
+ * nk_dot: *out = <a, b> (vector_vector_mul/mod.rs:32-34); nk_scale_acc: dst = beta*dst + x * (*scalar)
+ * with the scalar on the device (the 0-d gradient of vv, :58-63). */
+int nk_gemv(nk_ctx* ctx, int trans, int64_t rows, int64_t cols, const void* A, const void* x, float beta,
+            void* y, int ax_dtype, int y_dtype);
+int nk_outer_acc(nk_ctx* ctx, void* A, int a_dtype, const void* u, const void* v, int64_t rows,
+                 int64_t cols, int uv_dtype, float beta);
+int nk_dot(nk_ctx* ctx, float* out, const void* a, const void* b, size_t n, int dtype);
+int nk_scale_acc(nk_ctx* ctx, void* dst, int dst_dtype, const void* x, int x_dtype, const float* scalar,
+                 size_t n, float beta);
 
 /* ---- 2-D constant/zero padding of (planes, H, W) (pad/mod.rs:97-129, 157-182) ---- */
 int nk_pad2d_fwd(nk_ctx* ctx, void* y, const void* x, int64_t planes, int64_t h, int64_t w,
@@ -167,6 +221,21 @@ int nk_conv2d_bwd(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int dw_dtype,
                   float beta_dw, const void* g, const void* x, const void* w, int64_t n,
                   int64_t cin, int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw,
                   int64_t sh, int64_t sw, int64_t dh, int64_t dw, int64_t groups, int dtype);
+/* 1-D / 3-D convolution, x (N, Cin, s[0..nsp)), w (Cout, Cin/groups, k[0..nsp)), nsp = 1..3 sample dims
+ * (the reference's convolution is generic over them: convolution/mod.rs:85-226, goldens
+ * convolution/test.rs:144-239, 306-444 and the strided / dilated / grouped siblings).  CUDA-core gather
+ * kernels; the 2-D entry points above are the tensor-core path. */
+int nk_convnd_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, int nsp, int64_t n, int64_t cin,
+                  const int64_t* in_sp, int64_t cout, const int64_t* k, const int64_t* stride,
+                  const int64_t* dilation, int64_t groups, int dtype);
+int nk_convnd_bwd_input(nk_ctx* ctx, void* dx, const void* g, const void* w, int nsp, int64_t n,
+                        int64_t cin, const int64_t* in_sp, int64_t cout, const int64_t* k,
+                        const int64_t* stride, const int64_t* dilation, int64_t groups, int dtype,
+                        float beta);
+int nk_convnd_bwd_kernel(nk_ctx* ctx, void* dwt, int dw_dtype, const void* g, const void* x, int nsp,
+                         int64_t n, int64_t cin, const int64_t* in_sp, int64_t cout, const int64_t* k,
+                         const int64_t* stride, const int64_t* dilation, int64_t groups, int dtype,
+                         float beta);
 /* name of the kernel variant the last conv call used */
 const char* nk_last_conv_kernel(nk_ctx* ctx);
 
@@ -179,6 +248,41 @@ const char* nk_last_conv_kernel(nk_ctx* ctx);
 int nk_sgd_step(nk_ctx* ctx, void* w, int w_dtype, void* g, int g_dtype, float* buf, float* master,
                 size_t n, float lr, float l2, float momentum, float dampening, int nesterov,
                 float grad_scale, int write_back_grad);
+
+/* ---- Adam / AMSGrad / RMSProp / Adagrad as single fused passes (8-f rank 2; csrc/nk_optim.cu) ----
+ * Common to all: g' = grad_scale*g + l1*signum(w) + 2*l2*w (penalty.rs:63-79: L1, L2, ElasticNet), written
+ * back into g when write_back_grad (the reference adds the penalty into the gradient); state arrays are
+ * f32, n elements, zero before the first step; `master` as in nk_sgd_step.
+ *   adam     m = b1*m + (1-b1)g'; v = b2*v + (1-b2)g'^2; w -= m / (sqrt(v)/sqrt(1-b2^t) + eps) * lr/(1-b1^t)
+ *            (adam/mod.rs:131-169); max_exp_avg_sq != NULL -> AMSGrad: v^ = max(v^, v) replaces v in the
+ *            denominator (amsgrad/mod.rs:159-204).  `step` = t, counted from 1.
+ *   rmsprop  s = a*s + (1-a)g'^2; centered (grad_avg != NULL): ga = a*ga + (1-a)g', denom = sqrt(s - ga^2)+eps
+ *            else sqrt(s)+eps; momentum (> f32::EPSILON, buffer != NULL): b = mu*b + g'/denom, w -= lr*b;
+ *            else w -= g'/denom*lr (rmsprop/mod.rs:193-300).
+ *   adagrad  s += g'^2; w -= g' / (sqrt(s) + eps) * lr / (1 + (t-1)*lr_decay)   (adagrad/mod.rs:113-140). */
+int nk_adam_step(nk_ctx* ctx, void* w, int w_dtype, void* g, int g_dtype, float* exp_avg,
+                 float* exp_avg_sq, float* max_exp_avg_sq, float* master, size_t n, int64_t step, float lr,
+                 float beta1, float beta2, float eps, float l1, float l2, float grad_scale,
+                 int write_back_grad);
+int nk_rmsprop_step(nk_ctx* ctx, void* w, int w_dtype, void* g, int g_dtype, float* square_avg,
+                    float* grad_avg, float* momentum_buf, float* master, size_t n, float lr, float alpha,
+                    float eps, float momentum, float l1, float l2, float grad_scale, int write_back_grad);
+int nk_adagrad_step(nk_ctx* ctx, void* w, int w_dtype, void* g, int g_dtype, float* grad_sq, float* master,
+                    size_t n, int64_t step, float lr, float lr_decay, float eps, float l1, float l2,
+                    float grad_scale, int write_back_grad);
+
+/* ---- NCCL all-reduce behind the ABI (csrc/nk_comm.cu) ----
+ * The context owns the communicator; libnccl.so.2 is bound at run time (dlopen), so the library loads
+ * without it.  Rank 0 creates the 128-byte id and ships it to the others by any means; every rank then
+ * calls nk_comm_init_rank (collective).  nk_allreduce_sum sums `n` elements in place over the replicas,
+ * enqueued on the context stream (ordered with the kernels that produced the gradients and with the
+ * nk_sgd_step that follows).  Errors: NK_ERR_NCCL. */
+int nk_comm_unique_id(nk_ctx* ctx, void* id128);
+int nk_comm_init_rank(nk_ctx* ctx, int world, int rank, const void* id128);
+int nk_comm_destroy(nk_ctx* ctx);
+int nk_comm_world(nk_ctx* ctx);
+int nk_comm_rank(nk_ctx* ctx);
+int nk_allreduce_sum(nk_ctx* ctx, void* ptr, size_t n, int dtype);
 
 /* ---- data-parallel gradient exchange over NVLink peer memory ----
  * The reference has no multi-device path; under data parallel the only exchange on the hot path is

@@ -85,6 +85,33 @@ int nkg_convolution(nkg_var* kernel, nkg_var* input, int64_t sh, int64_t sw, int
 /* (N, C, H, W) -> (N, C*H*W): bit-exact view; not in the reference (SURVEY.md 2.2 "missing") */
 int nkg_flatten(nkg_var* a, nkg_var** out);
 
+/* ---- the rest of the op surface: broadcasting arithmetic (vardiff.rs Sub/Mul/Div impls over
+ * subtraction/, multiplication/, division/), unary maths (var.rs `exp`, `ln`, `sqrt`, `sigmoid`, `tanh`, `softplus`,
+ * `leaky_relu`, `pow(i32)`, `Neg`), `t()` (reverses every axis), n-d padding with a mode, mv / vm / vv and 1-d / 3-d
+ * convolution.  nkg_unary takes an nk_unary_op; the named functions are the reference's method names. */
+int nkg_sub(nkg_var* a, nkg_var* b, nkg_var** out);
+int nkg_mul(nkg_var* a, nkg_var* b, nkg_var** out);
+int nkg_div(nkg_var* a, nkg_var* b, nkg_var** out);
+int nkg_unary(nkg_var* a, int op, int iparam, nkg_var** out);
+int nkg_neg(nkg_var* a, nkg_var** out);
+int nkg_exp(nkg_var* a, nkg_var** out);
+int nkg_ln(nkg_var* a, nkg_var** out);
+int nkg_sqrt(nkg_var* a, nkg_var** out);
+int nkg_sigmoid(nkg_var* a, nkg_var** out);
+int nkg_tanh(nkg_var* a, nkg_var** out);
+int nkg_softplus(nkg_var* a, nkg_var** out);
+int nkg_leaky_relu(nkg_var* a, nkg_var** out);
+int nkg_pow(nkg_var* a, int exp, nkg_var** out);
+int nkg_transpose(nkg_var* a, nkg_var** out);
+/* pad the nsp (1..3) sample dims of (N, C, ...) with an nk_pad_mode (pad/mod.rs:20-182) */
+int nkg_pad_mode(nkg_var* a, int nsp, const int64_t* padding, int mode, float value, nkg_var** out);
+int nkg_mv(nkg_var* matrix, nkg_var* vector, nkg_var** out);   /* matrix_vector_mul/mod.rs */
+int nkg_vm(nkg_var* vector, nkg_var* matrix, nkg_var** out);   /* vector_matrix_mul/mod.rs */
+int nkg_vv(nkg_var* a, nkg_var* b, nkg_var** out);             /* vector_vector_mul/mod.rs: 0-d result */
+/* 1-d (N,C,L) / 3-d (N,C,D,H,W) convolution; the receiver is the kernel, as in nkg_convolution */
+int nkg_convolution_nd(nkg_var* kernel, nkg_var* input, int nsp, const int64_t* stride, const int64_t* dilation,
+                       int64_t groups, nkg_var** out);
+
 /* ---- gradient-ready hook (data parallel overlap): `cb(user, begin, end)` is called from inside nkg_backward(), on
  * the calling thread, right after the LAST kernel that accumulates into elements [begin, end) of this leaf's gradient
  * in the running backward pass has been launched -- so the caller can start the all-reduce of that range while the
@@ -104,6 +131,15 @@ int nkg_set_grad_rs(nkg_var* leaf, int world, int rank, void* const* slots, nkg_
 /* ---- SGD on a leaf (neuronika-optim/src/sgd/mod.rs:191-231) ---- */
 int nkg_sgd_step(nkg_var* param, float* momentum_buf, float* master, float lr, float l2, float momentum,
                  float dampening, int nesterov, float grad_scale);
+
+/* ---- Adam / AMSGrad / RMSProp / Adagrad on a leaf (neuronika-optim/src/{adam,amsgrad,rmsprop,adagrad}/mod.rs);
+ * state arrays are caller-owned f32 device buffers of the parameter's size (see nk_b200.h nk_adam_step ...) */
+int nkg_adam_step(nkg_var* param, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, float* master,
+                  int64_t step, float lr, float beta1, float beta2, float eps, float l1, float l2, float grad_scale);
+int nkg_rmsprop_step(nkg_var* param, float* square_avg, float* grad_avg, float* momentum_buf, float* master, float lr,
+                     float alpha, float eps, float momentum, float l1, float l2, float grad_scale);
+int nkg_adagrad_step(nkg_var* param, float* grad_sq, float* master, int64_t step, float lr, float lr_decay, float eps,
+                     float l1, float l2, float grad_scale);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,10 @@ LIB_PATH = os.path.join(_HERE, "libnk_b200.so")
 
 NK_F32, NK_BF16 = 0, 1
 NK_GEMM_AUTO, NK_GEMM_SIMT, NK_GEMM_TCGEN05 = 0, 1, 2
+NK_BIN_ADD, NK_BIN_SUB, NK_BIN_MUL, NK_BIN_DIV = 0, 1, 2, 3
+(NK_UN_NEG, NK_UN_EXP, NK_UN_LN, NK_UN_SQRT, NK_UN_SIGMOID, NK_UN_TANH, NK_UN_SOFTPLUS, NK_UN_LEAKY_RELU,
+ NK_UN_POWI) = range(9)
+NK_PAD_CONSTANT, NK_PAD_REFLECTIVE, NK_PAD_REPLICATIVE = 0, 1, 2
 NK_OK = 0
 NK_ERR = {-1: "NK_ERR_INVALID_ARG", -2: "NK_ERR_CUDA", -3: "NK_ERR_NCCL", -4: "NK_ERR_OOM",
           -5: "NK_ERR_UNSUPPORTED"}
@@ -79,8 +83,8 @@ _PROTOS = {
     "nk_log_softmax_bwd": (i32, [vp, vp, vp, vp, i64, i64, i64, i32, f32]),
     "nk_mse_fwd": (i32, [vp, vp, vp, vp, sz, i32, i32]),
     "nk_mse_bwd": (i32, [vp, vp, vp, vp, vp, sz, i32, i32, f32]),
-    "nk_nll_fwd": (i32, [vp, vp, vp, vp, i64, i64, i32, i32]),
-    "nk_nll_bwd": (i32, [vp, vp, vp, vp, i64, i64, i32, i32, f32]),
+    "nk_nll_fwd": (i32, [vp, vp, vp, vp, i32, i64, i64, i32, i32]),
+    "nk_nll_bwd": (i32, [vp, vp, vp, i32, vp, i64, i64, i32, i32, f32]),
     "nk_sum_fwd": (i32, [vp, vp, vp, sz, i32, i32]),
     "nk_sum_bwd": (i32, [vp, vp, vp, sz, i32, i32, f32]),
     "nk_pad2d_fwd": (i32, [vp, vp, vp, i64, i64, i64, i64, i64, f32, i32]),
@@ -97,6 +101,29 @@ _PROTOS = {
     "nk_peer_barrier": (i32, [vp, pvp, i32, i32, C.c_uint32]),
     "nk_gemm_rs": (i32, [vp, i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, pvp, i32, i32, i32]),
     "nk_reduce_bcast": (i32, [vp, vp, pvp, i32, i32, i64, i32]),
+    "nk_binary_bcast_fwd": (i32, [vp, i32, vp, vp, vp, i32, i32, pi64, i32, pi64, i32, pi64]),
+    "nk_binary_bcast_bwd": (i32, [vp, i32, i32, vp, i32, vp, vp, vp, i32, i32, pi64, i32, pi64, f32]),
+    "nk_unary_fwd": (i32, [vp, i32, vp, vp, sz, i32, i32]),
+    "nk_unary_bwd": (i32, [vp, i32, vp, vp, vp, sz, i32, i32, f32]),
+    "nk_transpose": (i32, [vp, vp, i32, vp, i32, i32, pi64, f32]),
+    "nk_padnd_fwd": (i32, [vp, vp, vp, i64, i32, pi64, pi64, i32, f32, i32]),
+    "nk_padnd_bwd": (i32, [vp, vp, vp, i64, i32, pi64, pi64, i32, f32]),
+    "nk_gemv": (i32, [vp, i32, i64, i64, vp, vp, f32, vp, i32, i32]),
+    "nk_outer_acc": (i32, [vp, vp, i32, vp, vp, i64, i64, i32, f32]),
+    "nk_dot": (i32, [vp, vp, vp, vp, sz, i32]),
+    "nk_scale_acc": (i32, [vp, vp, i32, vp, i32, vp, sz, f32]),
+    "nk_convnd_fwd": (i32, [vp, vp, vp, vp, i32, i64, i64, pi64, i64, pi64, pi64, pi64, i64, i32]),
+    "nk_convnd_bwd_input": (i32, [vp, vp, vp, vp, i32, i64, i64, pi64, i64, pi64, pi64, pi64, i64, i32, f32]),
+    "nk_convnd_bwd_kernel": (i32, [vp, vp, i32, vp, vp, i32, i64, i64, pi64, i64, pi64, pi64, pi64, i64, i32, f32]),
+    "nk_adam_step": (i32, [vp, vp, i32, vp, i32, vp, vp, vp, vp, sz, i64, f32, f32, f32, f32, f32, f32, f32, i32]),
+    "nk_rmsprop_step": (i32, [vp, vp, i32, vp, i32, vp, vp, vp, vp, sz, f32, f32, f32, f32, f32, f32, f32, i32]),
+    "nk_adagrad_step": (i32, [vp, vp, i32, vp, i32, vp, vp, sz, i64, f32, f32, f32, f32, f32, f32, i32]),
+    "nk_comm_unique_id": (i32, [vp, vp]),
+    "nk_comm_init_rank": (i32, [vp, i32, i32, vp]),
+    "nk_comm_destroy": (i32, [vp]),
+    "nk_comm_world": (i32, [vp]),
+    "nk_comm_rank": (i32, [vp]),
+    "nk_allreduce_sum": (i32, [vp, vp, sz, i32]),
     "nk_sgd_step": (i32, [vp, vp, i32, vp, i32, vp, vp, sz, f32, f32, f32, f32, i32, f32, i32]),
 }
 
@@ -131,7 +158,10 @@ def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
     x = np.ascontiguousarray(x, dtype=np.float32)
     bits = x.view(np.uint32).astype(np.uint64)
     bias = ((bits >> 16) & 1) + 0x7FFF
-    return ((bits + bias) >> 16).astype(np.uint16).reshape(x.shape)
+    out = ((bits + bias) >> 16).astype(np.uint16)
+    if np.any(np.isnan(x)):   # the rounding carry would turn a NaN with a high mantissa into +-0 / inf: keep it a quiet NaN
+        out = np.where(np.isnan(x), ((x.view(np.uint32) >> 16) | 0x0040).astype(np.uint16), out.reshape(x.shape))
+    return out.reshape(x.shape)
 
 
 def bf16_bits_to_f32(b: np.ndarray) -> np.ndarray:

@@ -97,6 +97,7 @@ int nk_ctx_destroy(nk_ctx* ctx) {
   if (!ctx) return NK_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  nk_comm_destroy(ctx);
   if (ctx->workspace) cudaFree(ctx->workspace);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

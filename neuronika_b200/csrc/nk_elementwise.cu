@@ -384,13 +384,13 @@ __global__ void reduce_stage2(float* __restrict__ out, const double* __restrict_
   if (threadIdx.x == 0) *out = float(s * scale);
 }
 
-template <typename T>
+template <typename T, typename TT>
 __global__ void __launch_bounds__(kThreads) nll_fwd_kernel(double* __restrict__ partials, const T* __restrict__ logp,
-                                                          const T* __restrict__ target, int64_t n, int64_t c) {
+                                                          const TT* __restrict__ target, int64_t n, int64_t c) {
   double acc = 0.0;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    int64_t cls = (int64_t)nk_to_f32<T>(target[i]);  // `target as usize`, nll/mod.rs:55
+    int64_t cls = (int64_t)nk_to_f32<TT>(target[i]);  // `target as usize`, nll/mod.rs:55
     if (cls >= 0 && cls < c) acc += double(nk_to_f32<T>(logp[i * c + cls]));
   }
 #pragma unroll
@@ -405,8 +405,8 @@ __global__ void __launch_bounds__(kThreads) nll_fwd_kernel(double* __restrict__ 
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads) nll_bwd_kernel(T* __restrict__ d, const T* __restrict__ target,
+template <typename T, typename TT>
+__global__ void __launch_bounds__(kThreads) nll_bwd_kernel(T* __restrict__ d, const TT* __restrict__ target,
                                                           const float* __restrict__ g, int64_t n, int64_t c,
                                                           float scale, float beta) {
   const int64_t total = n * c;
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(kThreads) nll_bwd_kernel(T* __restrict__ d, co
   const float gv = (*g) * scale;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t row = i / c, col = i - row * c;
-    const int64_t cls = (int64_t)nk_to_f32<T>(target[row]);
+    const int64_t cls = (int64_t)nk_to_f32<TT>(target[row]);
     float v = (cls == col) ? -gv : 0.f;
     if (beta != 0.f) v += beta * nk_to_f32<T>(d[i]);
     d[i] = nk_from_f32<T>(v);
@@ -786,36 +786,58 @@ int nk_mse_bwd(nk_ctx* ctx, void* dx, const void* x, const void* t, const float*
   NK_DISPATCH_DTYPE(dtype, T, return (launch_ew<T, 2>(ctx, "mse_bwd", dx, x, t, nullptr, n, beta, op)));
 }
 
-int nk_nll_fwd(nk_ctx* ctx, float* loss, const void* logp, const void* target, int64_t n, int64_t c, int dtype,
-               int mean) {
+static int nll_target_ok(nk_ctx* ctx, int target_dtype, int64_t c) {
+  NK_REQUIRE(ctx, nk_dtype_ok(target_dtype), "nll: bad target dtype %d", target_dtype);
+  // bf16 holds integers exactly only up to 256: larger class ids would silently select the wrong class
+  NK_REQUIRE(ctx, target_dtype == NK_F32 || c <= 256, "nll: a bf16 target cannot hold class ids above 256 (c = %lld); "
+             "pass the target as f32", (long long)c);
+  return NK_OK;
+}
+
+int nk_nll_fwd(nk_ctx* ctx, float* loss, const void* logp, const void* target, int target_dtype, int64_t n, int64_t c,
+               int dtype, int mean) {
   if (!ctx) return NK_ERR_INVALID_ARG;
   NK_REQUIRE(ctx, nk_dtype_ok(dtype), "nk_nll_fwd: bad dtype %d", dtype);
   NK_REQUIRE(ctx, loss && logp && target && n > 0 && c > 0, "nk_nll_fwd: NULL pointer or empty input");
+  int rc = nll_target_ok(ctx, target_dtype, c);
+  if (rc) return rc;
   int blocks = ew_blocks(ctx, size_t(n));
   double* partials;
-  int rc = nk_workspace(ctx, size_t(blocks) * sizeof(double), (void**)&partials);
+  rc = nk_workspace(ctx, size_t(blocks) * sizeof(double), (void**)&partials);
   if (rc) return rc;
-  if (dtype == NK_BF16)
-    nll_fwd_kernel<__nv_bfloat16><<<blocks, kThreads, 0, ctx->stream>>>(partials, (const __nv_bfloat16*)logp, (const __nv_bfloat16*)target, n, c);
+  using B = __nv_bfloat16;
+  if (dtype == NK_BF16 && target_dtype == NK_BF16)
+    nll_fwd_kernel<B, B><<<blocks, kThreads, 0, ctx->stream>>>(partials, (const B*)logp, (const B*)target, n, c);
+  else if (dtype == NK_BF16)
+    nll_fwd_kernel<B, float><<<blocks, kThreads, 0, ctx->stream>>>(partials, (const B*)logp, (const float*)target, n, c);
+  else if (target_dtype == NK_BF16)
+    nll_fwd_kernel<float, B><<<blocks, kThreads, 0, ctx->stream>>>(partials, (const float*)logp, (const B*)target, n, c);
   else
-    nll_fwd_kernel<float><<<blocks, kThreads, 0, ctx->stream>>>(partials, (const float*)logp, (const float*)target, n, c);
+    nll_fwd_kernel<float, float><<<blocks, kThreads, 0, ctx->stream>>>(partials, (const float*)logp, (const float*)target, n, c);
   NK_LAUNCHED(ctx, "nll_fwd");
   reduce_stage2<<<1, 32, 0, ctx->stream>>>(loss, partials, blocks, mean ? -1.0 / double(n) : -1.0);
   NK_LAUNCHED(ctx, "reduce_stage2");
   return NK_OK;
 }
 
-int nk_nll_bwd(nk_ctx* ctx, void* dlogp, const void* target, const float* g, int64_t n, int64_t c, int dtype,
-               int mean, float beta) {
+int nk_nll_bwd(nk_ctx* ctx, void* dlogp, const void* target, int target_dtype, const float* g, int64_t n, int64_t c,
+               int dtype, int mean, float beta) {
   if (!ctx) return NK_ERR_INVALID_ARG;
   NK_REQUIRE(ctx, nk_dtype_ok(dtype), "nk_nll_bwd: bad dtype %d", dtype);
   NK_REQUIRE(ctx, dlogp && target && g && n > 0 && c > 0, "nk_nll_bwd: NULL pointer or empty input");
+  int rc = nll_target_ok(ctx, target_dtype, c);
+  if (rc) return rc;
   int blocks = ew_blocks(ctx, size_t(n * c));
   float scale = mean ? 1.f / float(n) : 1.f;
-  if (dtype == NK_BF16)
-    nll_bwd_kernel<__nv_bfloat16><<<blocks, kThreads, 0, ctx->stream>>>((__nv_bfloat16*)dlogp, (const __nv_bfloat16*)target, g, n, c, scale, beta);
+  using B = __nv_bfloat16;
+  if (dtype == NK_BF16 && target_dtype == NK_BF16)
+    nll_bwd_kernel<B, B><<<blocks, kThreads, 0, ctx->stream>>>((B*)dlogp, (const B*)target, g, n, c, scale, beta);
+  else if (dtype == NK_BF16)
+    nll_bwd_kernel<B, float><<<blocks, kThreads, 0, ctx->stream>>>((B*)dlogp, (const float*)target, g, n, c, scale, beta);
+  else if (target_dtype == NK_BF16)
+    nll_bwd_kernel<float, B><<<blocks, kThreads, 0, ctx->stream>>>((float*)dlogp, (const B*)target, g, n, c, scale, beta);
   else
-    nll_bwd_kernel<float><<<blocks, kThreads, 0, ctx->stream>>>((float*)dlogp, (const float*)target, g, n, c, scale, beta);
+    nll_bwd_kernel<float, float><<<blocks, kThreads, 0, ctx->stream>>>((float*)dlogp, (const float*)target, g, n, c, scale, beta);
   NK_LAUNCHED(ctx, "nll_bwd");
   return NK_OK;
 }

@@ -109,6 +109,7 @@ struct Gradient {
   void* rs_user = nullptr;
   int last_writer = -1;             // index (in reverse tape order) of the last node writing it in this pass
   bool hook_fired = false;
+  bool is_leaf = false;             // created by requires_grad(): owned by the user, never aliased away by the peephole
   Gradient(nk_ctx* c, Shape s, int dt) : ctx(c), shape(std::move(s)), dtype(dt) {}
   ~Gradient() {
     if (owned && ptr) nk_free(ctx, ptr);
@@ -220,6 +221,31 @@ static void gemm(nk_ctx* ctx, bool ta, bool tb, int64_t M, int64_t N, int64_t K,
   ck(ctx, nk_gemm_bias_act(ctx, ta, tb, M, N, K, 1.f, A, lda, B, ldb, beta, C, N, ab_dt, c_dt, bias, bias_dt, relu));
 }
 
+// A backward kernel that produces its result in element type `kdt` accumulating into a gradient that may have another
+// element type (a bf16 leaf with an f32 gradient, requires_grad(grad_dtype)): same type -> the kernel writes the
+// gradient directly with the accumulate mode `beta`; otherwise it writes a temporary (beta = 0) which is then added
+// with the mixed-type axpy of nk_unbroadcast_acc.
+template <typename F>
+static void acc_typed(nk_ctx* ctx, const GradientP& g, int kdt, F&& kernel) {
+  float beta;
+  void* d = g->acc(&beta);
+  if (g->dtype == kdt) {
+    kernel(d, beta);
+    return;
+  }
+  void* tmp = nullptr;
+  ck(ctx, nk_alloc_uninit(ctx, size_t(g->n()) * esize(kdt), &tmp));
+  try {
+    kernel(tmp, 0.f);
+    ck(ctx, nk_unbroadcast_acc(ctx, d, g->dtype, (int)g->shape.size(), g->shape.data(), tmp, kdt, (int)g->shape.size(),
+                               g->shape.data(), beta));
+  } catch (...) {
+    nk_free(ctx, tmp);
+    throw;
+  }
+  ck(ctx, nk_free(ctx, tmp));
+}
+
 // ------------------------------------------------------------------------------- matmul nodes
 // MatrixMatrixMul (matrix_matrix_mul/mod.rs:11-41) and MatrixMatrixMulT (matrix_matrix_mul_t/mod.rs:11-41)
 struct MatMul : Forward {
@@ -268,7 +294,7 @@ struct MatMulBackward : Backward {
         // data parallel: the epilogue of the dW GEMM pushes each row shard to its owner over NVLink (nk_gemm_rs);
         // only when this node alone produces the gradient in this pass and the gradient starts from zero
         const bool push = beta == 0.f && gdt == NK_BF16 && right_grad->dtype == NK_F32 && r == right_grad.get() &&
-                          r->writers == 1 && rows % (int64_t(r->rs_world) * 128) == 0;
+                          r->writers == 1 && rows % (int64_t(r->rs_world) * 128) == 0 && cols > 128 && cols % 8 == 0;
         if (push)
           ck(ctx, nk_gemm_rs(ctx, 1, 0, rows, cols, M, 1.f, A, rows, B, cols, r->rs_slots, r->rs_world, r->rs_rank, gdt));
         else
@@ -376,10 +402,10 @@ struct ReLUBackward : Backward {  // relu/mod.rs:40-79
     if (operand_grad) out.push_back(operand_grad->root());
   }
   void backward() override {
-    float beta;
-    void* d = operand_grad->acc(&beta);
-    ck(ctx, nk_relu_bwd(ctx, d, operand_data->rptr(), gradient->get(), size_t(operand_data->n()),
-                        operand_data->dtype, beta));
+    const void* g = gradient->get();
+    acc_typed(ctx, operand_grad, operand_data->dtype, [&](void* d, float beta) {
+      ck(ctx, nk_relu_bwd(ctx, d, operand_data->rptr(), g, size_t(operand_data->n()), operand_data->dtype, beta));
+    });
   }
 };
 
@@ -415,10 +441,10 @@ struct SoftmaxBackward : Backward {  // softmax/mod.rs:55-104, logsoftmax/mod.rs
   void backward() override {
     int64_t o, l, i;
     lanes(data->shape, axis, o, l, i);
-    float beta;
-    void* d = operand_grad->acc(&beta);
-    ck(ctx, (log ? nk_log_softmax_bwd : nk_softmax_bwd)(ctx, d, data->rptr(), gradient->get(), o, l, i, data->dtype,
-                                                         beta));
+    const void* g = gradient->get();
+    acc_typed(ctx, operand_grad, data->dtype, [&](void* d, float beta) {
+      ck(ctx, (log ? nk_log_softmax_bwd : nk_softmax_bwd)(ctx, d, data->rptr(), g, o, l, i, data->dtype, beta));
+    });
   }
 };
 
@@ -455,8 +481,8 @@ struct Loss : Forward {  // squared_error/mod.rs:11-58, nll/mod.rs:11-68
   const char* name() const override { return nll ? "NegativeLogLikelihood" : "SquaredError"; }
   void forward() override {
     if (nll)
-      ck(ctx, nk_nll_fwd(ctx, (float*)data->wptr(), input->rptr(), target->rptr(), input->shape[0], input->shape[1],
-                         input->dtype, mean));
+      ck(ctx, nk_nll_fwd(ctx, (float*)data->wptr(), input->rptr(), target->rptr(), target->dtype, input->shape[0],
+                         input->shape[1], input->dtype, mean));
     else
       ck(ctx, nk_mse_fwd(ctx, (float*)data->wptr(), input->rptr(), target->rptr(), size_t(input->n()), input->dtype,
                          mean));
@@ -472,13 +498,14 @@ struct LossBackward : Backward {  // squared_error/mod.rs:60-122, nll/mod.rs:70-
     if (input_grad) out.push_back(input_grad->root());
   }
   void backward() override {
-    float beta;
-    void* d = input_grad->acc(&beta);
     const float* g = (const float*)gradient->get();
-    if (nll)
-      ck(ctx, nk_nll_bwd(ctx, d, target->rptr(), g, input->shape[0], input->shape[1], input->dtype, mean, beta));
-    else
-      ck(ctx, nk_mse_bwd(ctx, d, input->rptr(), target->rptr(), g, size_t(input->n()), input->dtype, mean, beta));
+    acc_typed(ctx, input_grad, input->dtype, [&](void* d, float beta) {
+      if (nll)
+        ck(ctx, nk_nll_bwd(ctx, d, target->rptr(), target->dtype, g, input->shape[0], input->shape[1], input->dtype,
+                           mean, beta));
+      else
+        ck(ctx, nk_mse_bwd(ctx, d, input->rptr(), target->rptr(), g, size_t(input->n()), input->dtype, mean, beta));
+    });
   }
 };
 
@@ -504,9 +531,10 @@ struct PadBackward : Backward {  // pad/mod.rs:131-182
   }
   void backward() override {
     const Shape& s = operand_grad->shape;
-    float beta;
-    void* d = operand_grad->acc(&beta);
-    ck(ctx, nk_pad2d_bwd(ctx, d, gradient->get(), s[0] * s[1], s[2], s[3], ph, pw, operand_grad->dtype, beta));
+    const void* g = gradient->get();
+    acc_typed(ctx, operand_grad, gradient->dtype, [&](void* d, float beta) {
+      ck(ctx, nk_pad2d_bwd(ctx, d, g, s[0] * s[1], s[2], s[3], ph, pw, gradient->dtype, beta));
+    });
   }
 };
 
@@ -553,7 +581,10 @@ struct ConvolutionBackward : Backward {  // convolution/mod.rs:357-510: input fi
                                    gradient->shape.data(), bbeta));
       }
     }
-    if (input_grad && kernel_grad) {  // both halves: one pass over the output gradient where the kernels allow it
+    // dX is produced in the element type of the output gradient; an input gradient of another type goes through
+    // acc_typed (and then the two halves run as separate kernels)
+    const bool dx_same = !input_grad || input_grad->dtype == gradient->dtype;
+    if (input_grad && kernel_grad && dx_same) {  // both halves: one pass over the output gradient where the kernels allow it
       float bx, bw;
       void* dxp = input_grad->acc(&bx);
       void* dwp = kernel_grad->acc(&bw);
@@ -562,21 +593,291 @@ struct ConvolutionBackward : Backward {  // convolution/mod.rs:357-510: input fi
                             gradient->dtype));
       grad_written(kernel_grad);
       grad_written(input_grad);
-    } else if (input_grad) {
-      float beta;
-      void* d = input_grad->acc(&beta);
-      ck(ctx, nk_conv2d_bwd_input(ctx, d, gradient->get(), kernel->rptr(), a.n, a.cin, a.h, a.w, a.cout, a.kh, a.kw,
-                                  a.sh, a.sw, a.dh, a.dw, a.groups, gradient->dtype, beta));
-      grad_written(input_grad);
-    } else if (kernel_grad) {
-      float beta;
-      void* d = kernel_grad->acc(&beta);
-      ck(ctx, nk_conv2d_bwd_kernel(ctx, d, kernel_grad->dtype, dbias, gradient->get(), input->rptr(), a.n, a.cin,
-                                   a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups, gradient->dtype,
-                                   beta));
-      grad_written(kernel_grad);
+    } else {
+      if (input_grad) {
+        const void* g = gradient->get();
+        acc_typed(ctx, input_grad, gradient->dtype, [&](void* d, float beta) {
+          ck(ctx, nk_conv2d_bwd_input(ctx, d, g, kernel->rptr(), a.n, a.cin, a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw,
+                                      a.dh, a.dw, a.groups, gradient->dtype, beta));
+        });
+        grad_written(input_grad);
+      }
+      if (kernel_grad) {
+        float beta;
+        void* d = kernel_grad->acc(&beta);
+        ck(ctx, nk_conv2d_bwd_kernel(ctx, d, kernel_grad->dtype, dbias, gradient->get(), input->rptr(), a.n, a.cin,
+                                     a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups, gradient->dtype,
+                                     beta));
+        grad_written(kernel_grad);
+      }
     }
     if (bias_grad) grad_written(bias_grad);
+  }
+};
+
+// ------------------------------------------------------------------------------- sub / mul / div (broadcasting)
+// subtraction/mod.rs:11-172, multiplication/mod.rs:11-185, division/mod.rs:11-185
+struct Binary : Forward {
+  nk_ctx* ctx;
+  TensorP left, right, data;
+  int op;
+  const char* name() const override {
+    return op == NK_BIN_SUB ? "Subtraction" : op == NK_BIN_MUL ? "Multiplication" : "Division";
+  }
+  void forward() override {
+    ck(ctx, nk_binary_bcast_fwd(ctx, op, data->wptr(), left->rptr(), right->rptr(), data->dtype, (int)data->shape.size(),
+                                data->shape.data(), (int)left->shape.size(), left->shape.data(),
+                                (int)right->shape.size(), right->shape.data()));
+  }
+};
+struct BinaryBackward : Backward {
+  nk_ctx* ctx;
+  TensorP left_data, right_data;
+  GradientP left_grad, right_grad;  // either may be null
+  int op;
+  const char* name() const override {
+    return op == NK_BIN_SUB ? "SubtractionBackward" : op == NK_BIN_MUL ? "MultiplicationBackward" : "DivisionBackward";
+  }
+  void targets(std::vector<Gradient*>& out) override {
+    if (left_grad) out.push_back(left_grad->root());
+    if (right_grad) out.push_back(right_grad->root());
+  }
+  void side(int sd, const GradientP& dst) {
+    if (!dst) return;
+    float beta;
+    void* d = dst->acc(&beta);
+    ck(ctx, nk_binary_bcast_bwd(ctx, op, sd, d, dst->dtype, gradient->get(), left_data->rptr(), right_data->rptr(),
+                                gradient->dtype, (int)left_data->shape.size(), left_data->shape.data(),
+                                (int)right_data->shape.size(), right_data->shape.data(), beta));
+    grad_written(dst);
+  }
+  void backward() override {  // left first, then right, like the composite nodes (e.g. multiplication/mod.rs:176-181)
+    side(0, left_grad);
+    side(1, right_grad);
+  }
+};
+
+// ------------------------------------------------------------------------------- unary family
+// negation, exp, logn, sqrt, sigmoid, tanh, softplus, leaky_relu, power (node/*/mod.rs; see nk_b200.h nk_unary_*)
+static const char* unary_name(int op, bool bwd) {
+  static const char* f[] = {"Negation", "Exp", "Logn", "Sqrt", "Sigmoid", "TanH", "SoftPlus", "LeakyReLU", "Power"};
+  static const char* b[] = {"NegationBackward", "ExpBackward", "LognBackward", "SqrtBackward", "SigmoidBackward",
+                            "TanHBackward", "SoftPlusBackward", "LeakyReLUBackward", "PowerBackward"};
+  return (bwd ? b : f)[op];
+}
+struct Unary : Forward {
+  nk_ctx* ctx;
+  TensorP operand, data;
+  int op, iparam;
+  const char* name() const override { return unary_name(op, false); }
+  void forward() override {
+    ck(ctx, nk_unary_fwd(ctx, op, data->wptr(), operand->rptr(), size_t(data->n()), data->dtype, iparam));
+  }
+};
+struct UnaryBackward : Backward {
+  nk_ctx* ctx;
+  TensorP saved;  // the node's output (exp, sqrt, sigmoid, tanh) or its input (ln, softplus, leaky_relu, powi)
+  GradientP operand_grad;
+  int op, iparam;
+  const char* name() const override { return unary_name(op, true); }
+  void targets(std::vector<Gradient*>& out) override {
+    if (operand_grad) out.push_back(operand_grad->root());
+  }
+  void backward() override {
+    const void* g = gradient->get();
+    const void* sv = saved ? saved->rptr() : nullptr;
+    acc_typed(ctx, operand_grad, gradient->dtype, [&](void* d, float beta) {
+      ck(ctx, nk_unary_bwd(ctx, op, d, sv, g, size_t(gradient->n()), gradient->dtype, iparam, beta));
+    });
+    grad_written(operand_grad);
+  }
+};
+
+// ------------------------------------------------------------------------------- transpose (transpose/mod.rs:11-75)
+struct Transpose : Forward {
+  nk_ctx* ctx;
+  TensorP operand, data;
+  const char* name() const override { return "Transpose"; }
+  void forward() override {
+    ck(ctx, nk_transpose(ctx, data->wptr(), data->dtype, operand->rptr(), operand->dtype, (int)operand->shape.size(),
+                         operand->shape.data(), 0.f));
+  }
+};
+struct TransposeBackward : Backward {
+  nk_ctx* ctx;
+  GradientP operand_grad;
+  const char* name() const override { return "TransposeBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (operand_grad) out.push_back(operand_grad->root());
+  }
+  void backward() override {  // dX += G^T
+    float beta;
+    void* d = operand_grad->acc(&beta);
+    ck(ctx, nk_transpose(ctx, d, operand_grad->dtype, gradient->get(), gradient->dtype, (int)gradient->shape.size(),
+                         gradient->shape.data(), beta));
+    grad_written(operand_grad);
+  }
+};
+
+// ------------------------------------------------------------------------------- n-d padding with a mode
+// Pad<D, T: PaddingMode> over (N, C, s...) with 1..3 sample dims (pad/mod.rs:20-182; modes pad/{constant,zero,
+// reflective,replicative}/mod.rs).  The 2-d constant case keeps its own node (Pad above).
+struct PadNd : Forward {
+  nk_ctx* ctx;
+  TensorP operand, data;
+  int nsp, mode;
+  int64_t pad[3];
+  float value;
+  const char* name() const override { return "Pad"; }
+  void forward() override {
+    const Shape& s = operand->shape;
+    ck(ctx, nk_padnd_fwd(ctx, data->wptr(), operand->rptr(), s[0] * s[1], nsp, s.data() + 2, pad, mode, value,
+                         data->dtype));
+  }
+};
+struct PadNdBackward : Backward {
+  nk_ctx* ctx;
+  GradientP operand_grad;
+  int nsp;
+  int64_t pad[3];
+  const char* name() const override { return "PadBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (operand_grad) out.push_back(operand_grad->root());
+  }
+  void backward() override {
+    const Shape& s = operand_grad->shape;
+    const void* g = gradient->get();
+    acc_typed(ctx, operand_grad, gradient->dtype, [&](void* d, float beta) {
+      ck(ctx, nk_padnd_bwd(ctx, d, g, s[0] * s[1], nsp, s.data() + 2, pad, gradient->dtype, beta));
+    });
+    grad_written(operand_grad);
+  }
+};
+
+// ------------------------------------------------------------------------------- mv / vm / vv
+// matrix_vector_mul/mod.rs:11-129, vector_matrix_mul/mod.rs:11-129, vector_vector_mul/mod.rs:11-91
+struct MatVec : Forward {
+  nk_ctx* ctx;
+  TensorP mat, vec, data;
+  bool vm;  // true: y = v.A
+  const char* name() const override { return vm ? "VectorMatrixMul" : "MatrixVectorMul"; }
+  void forward() override {
+    ck(ctx, nk_gemv(ctx, vm ? 1 : 0, mat->shape[0], mat->shape[1], mat->rptr(), vec->rptr(), 0.f, data->wptr(),
+                    mat->dtype, data->dtype));
+  }
+};
+struct MatVecBackward : Backward {
+  nk_ctx* ctx;
+  TensorP mat, vec;
+  GradientP mat_grad, vec_grad;
+  bool vm;
+  const char* name() const override { return vm ? "VectorMatrixMulBackward" : "MatrixVectorMulBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (mat_grad) out.push_back(mat_grad->root());
+    if (vec_grad) out.push_back(vec_grad->root());
+  }
+  void backward() override {
+    const void* g = gradient->get();
+    const int64_t rows = mat->shape[0], cols = mat->shape[1];
+    auto do_mat = [&] {
+      if (!mat_grad) return;
+      float beta;
+      void* d = mat_grad->acc(&beta);
+      // mv: dA += g (x) v ; vm: dA += v (x) g
+      ck(ctx, nk_outer_acc(ctx, d, mat_grad->dtype, vm ? vec->rptr() : g, vm ? g : vec->rptr(), rows, cols,
+                           gradient->dtype, beta));
+      grad_written(mat_grad);
+    };
+    auto do_vec = [&] {
+      if (!vec_grad) return;
+      float beta;
+      void* d = vec_grad->acc(&beta);
+      // mv: dv += A^T.g ; vm: dv += A.g
+      ck(ctx, nk_gemv(ctx, vm ? 0 : 1, rows, cols, mat->rptr(), g, beta, d, mat->dtype, vec_grad->dtype));
+      grad_written(vec_grad);
+    };
+    if (vm) {  // left operand first
+      do_vec();
+      do_mat();
+    } else {
+      do_mat();
+      do_vec();
+    }
+  }
+};
+struct VecVec : Forward {
+  nk_ctx* ctx;
+  TensorP left, right, data;
+  const char* name() const override { return "VectorVectorMul"; }
+  void forward() override {
+    ck(ctx, nk_dot(ctx, (float*)data->wptr(), left->rptr(), right->rptr(), size_t(left->n()), left->dtype));
+  }
+};
+struct VecVecBackward : Backward {
+  nk_ctx* ctx;
+  TensorP left, right;
+  GradientP left_grad, right_grad;
+  const char* name() const override { return "VectorVectorMulBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (left_grad) out.push_back(left_grad->root());
+    if (right_grad) out.push_back(right_grad->root());
+  }
+  void backward() override {
+    const float* g = (const float*)gradient->get();
+    auto one = [&](const GradientP& dst, const TensorP& other) {
+      if (!dst) return;
+      float beta;
+      void* d = dst->acc(&beta);
+      ck(ctx, nk_scale_acc(ctx, d, dst->dtype, other->rptr(), other->dtype, g, size_t(other->n()), beta));
+      grad_written(dst);
+    };
+    one(left_grad, right);
+    one(right_grad, left);
+  }
+};
+
+// ------------------------------------------------------------------------------- 1-d / 3-d convolution
+struct ConvNdArgs {
+  int nsp;
+  int64_t n, cin, cout, groups;
+  int64_t in[3], k[3], s[3], d[3];
+};
+struct ConvolutionNd : Forward {  // convolution/mod.rs:296-355 for Ix3 / Ix5 operands
+  nk_ctx* ctx;
+  TensorP input, kernel, data;
+  ConvNdArgs a;
+  const char* name() const override { return "Convolution"; }
+  void forward() override {
+    ck(ctx, nk_convnd_fwd(ctx, data->wptr(), input->rptr(), kernel->rptr(), a.nsp, a.n, a.cin, a.in, a.cout, a.k, a.s,
+                          a.d, a.groups, data->dtype));
+  }
+};
+struct ConvolutionNdBackward : Backward {  // convolution/mod.rs:357-510
+  nk_ctx* ctx;
+  TensorP input, kernel;
+  GradientP input_grad, kernel_grad;
+  ConvNdArgs a;
+  const char* name() const override { return "ConvolutionBackward"; }
+  void targets(std::vector<Gradient*>& out) override {
+    if (input_grad) out.push_back(input_grad->root());
+    if (kernel_grad) out.push_back(kernel_grad->root());
+  }
+  void backward() override {
+    const void* g = gradient->get();
+    if (input_grad) {
+      acc_typed(ctx, input_grad, gradient->dtype, [&](void* d, float beta) {
+        ck(ctx, nk_convnd_bwd_input(ctx, d, g, kernel->rptr(), a.nsp, a.n, a.cin, a.in, a.cout, a.k, a.s, a.d, a.groups,
+                                    gradient->dtype, beta));
+      });
+      grad_written(input_grad);
+    }
+    if (kernel_grad) {
+      float beta;
+      void* d = kernel_grad->acc(&beta);
+      ck(ctx, nk_convnd_bwd_kernel(ctx, d, kernel_grad->dtype, g, input->rptr(), a.nsp, a.n, a.cin, a.in, a.cout, a.k,
+                                   a.s, a.d, a.groups, gradient->dtype, beta));
+      grad_written(kernel_grad);
+    }
   }
 };
 
@@ -715,6 +1016,9 @@ void fuse(nkg_var* v) {
       if (!g || flag || g->alias || g->ptr) return;
       if (g->shape != ab->gradient->shape || g->dtype != ab->gradient->dtype) return;
       if (!g->owned) return;
+      // only a gradient produced by a Backward node may be aliased: a leaf's gradient belongs to the user (hooks and
+      // reduce-scatter plans sit on it, it accumulates over backward() calls and outlives this graph)
+      if (g->is_leaf || g->hook || g->rs_world > 1) return;
       if (g.use_count() != 2) return;  // the producer's Backward node + this node
       g->alias = ab->gradient;
       flag = true;
@@ -813,6 +1117,7 @@ int nkg_requires_grad(nkg_var* a, int grad_dtype, void* grad_ptr, nkg_var** out)
     if (!a || !out) fail(NK_ERR_INVALID_ARG, "nkg_requires_grad: NULL");
     nkg_var* v = new nkg_var(*a);  // shares data and forward tape (VarDiff::leaf(self, zeros))
     v->grad = std::make_shared<Gradient>(a->ctx, a->data->shape, grad_dtype < 0 ? a->data->dtype : grad_dtype);
+    v->grad->is_leaf = true;
     if (grad_ptr) {
       v->grad->ptr = grad_ptr;
       v->grad->owned = false;
@@ -1082,7 +1387,15 @@ int nkg_mean(nkg_var* a, nkg_var** out) { return summean_impl(a, true, out); }
 static int loss_impl(nkg_var* input, nkg_var* target, int reduction, bool nll, nkg_var** out) {
   return guard([&] {
     if (!input || !target || !out) fail(NK_ERR_INVALID_ARG, "loss: NULL");
-    require_same_dtype(input, target, nll ? "nll_loss" : "mse_loss");
+    if (nll) {
+      // class ids are stored as floats (nll/mod.rs:55 `target as usize`): an f32 target is accepted whatever the
+      // input's element type; a bf16 target represents integers exactly only up to 256
+      if (input->ctx != target->ctx) fail(NK_ERR_INVALID_ARG, "nll_loss: operands live on different devices");
+      if (target->data->dtype == NK_BF16 && input->data->shape.size() == 2 && input->data->shape[1] > 256)
+        fail(NK_ERR_INVALID_ARG, "nll_loss: a bf16 target cannot hold class ids above 256; pass the target as f32");
+    } else {
+      require_same_dtype(input, target, "mse_loss");
+    }
     if (nll) {
       if (input->data->shape.size() != 2 || target->data->shape.size() != 1 ||
           target->data->shape[0] != input->data->shape[0])
@@ -1213,6 +1526,296 @@ int nkg_flatten(nkg_var* a, nkg_var** out) {
     v->fwd_buf.clear();
     v->bwd_buf.clear();
     *out = v;
+  });
+}
+
+// ---------------------------------------------------------------- 8-f operators
+static int binary_impl(nkg_var* a, nkg_var* b, int op, nkg_var** out) {
+  return guard([&] {
+    if (!a || !b || !out) fail(NK_ERR_INVALID_ARG, "binary op: NULL");
+    require_same_dtype(a, b, op == NK_BIN_SUB ? "sub" : op == NK_BIN_MUL ? "mul" : "div");
+    Shape os = cobroadcast(a->data->shape, b->data->shape);
+    nkg_var* v = new_like(a);
+    merge(v, a, b);
+    v->data = std::make_shared<Tensor>(a->ctx, os, a->data->dtype);
+    auto fw = std::make_shared<Binary>();
+    fw->ctx = a->ctx;
+    fw->left = a->data;
+    fw->right = b->data;
+    fw->data = v->data;
+    fw->op = op;
+    uint64_t id = push(v, fw);
+    if (a->diff() || b->diff()) {
+      v->grad = std::make_shared<Gradient>(a->ctx, os, a->data->dtype);
+      auto bw = std::make_shared<BinaryBackward>();
+      bw->ctx = a->ctx;
+      bw->op = op;
+      bw->gradient = v->grad;
+      bw->left_data = a->data;
+      bw->right_data = b->data;
+      bw->left_grad = a->grad;
+      bw->right_grad = b->grad;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+int nkg_sub(nkg_var* a, nkg_var* b, nkg_var** out) { return binary_impl(a, b, NK_BIN_SUB, out); }
+int nkg_mul(nkg_var* a, nkg_var* b, nkg_var** out) { return binary_impl(a, b, NK_BIN_MUL, out); }
+int nkg_div(nkg_var* a, nkg_var* b, nkg_var** out) { return binary_impl(a, b, NK_BIN_DIV, out); }
+
+int nkg_unary(nkg_var* a, int op, int iparam, nkg_var** out) {
+  return guard([&] {
+    if (!a || !out) fail(NK_ERR_INVALID_ARG, "unary op: NULL");
+    if (op < NK_UN_NEG || op > NK_UN_POWI) fail(NK_ERR_INVALID_ARG, "unary op: bad op %d", op);
+    TensorP od;
+    nkg_var* v = unary_node(a, a->data->shape, a->data->dtype, od);
+    auto fw = std::make_shared<Unary>();
+    fw->ctx = a->ctx;
+    fw->operand = a->data;
+    fw->data = od;
+    fw->op = op;
+    fw->iparam = iparam;
+    uint64_t id = push(v, fw);
+    if (a->diff()) {
+      v->grad = std::make_shared<Gradient>(a->ctx, od->shape, od->dtype);
+      auto bw = std::make_shared<UnaryBackward>();
+      bw->ctx = a->ctx;
+      bw->gradient = v->grad;
+      bw->operand_grad = a->grad;
+      bw->op = op;
+      bw->iparam = iparam;
+      const bool keeps_output = op == NK_UN_EXP || op == NK_UN_SQRT || op == NK_UN_SIGMOID || op == NK_UN_TANH;
+      bw->saved = op == NK_UN_NEG ? nullptr : (keeps_output ? od : a->data);
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+int nkg_neg(nkg_var* a, nkg_var** out) { return nkg_unary(a, NK_UN_NEG, 0, out); }
+int nkg_exp(nkg_var* a, nkg_var** out) { return nkg_unary(a, NK_UN_EXP, 0, out); }
+int nkg_ln(nkg_var* a, nkg_var** out) { return nkg_unary(a, NK_UN_LN, 0, out); }
+int nkg_sqrt(nkg_var* a, nkg_var** out) { return nkg_unary(a, NK_UN_SQRT, 0, out); }
+int nkg_sigmoid(nkg_var* a, nkg_var** out) { return nkg_unary(a, NK_UN_SIGMOID, 0, out); }
+int nkg_tanh(nkg_var* a, nkg_var** out) { return nkg_unary(a, NK_UN_TANH, 0, out); }
+int nkg_softplus(nkg_var* a, nkg_var** out) { return nkg_unary(a, NK_UN_SOFTPLUS, 0, out); }
+int nkg_leaky_relu(nkg_var* a, nkg_var** out) { return nkg_unary(a, NK_UN_LEAKY_RELU, 0, out); }
+int nkg_pow(nkg_var* a, int exp, nkg_var** out) { return nkg_unary(a, NK_UN_POWI, exp, out); }
+
+int nkg_transpose(nkg_var* a, nkg_var** out) {
+  return guard([&] {
+    if (!a || !out) fail(NK_ERR_INVALID_ARG, "t: NULL");
+    Shape os(a->data->shape.rbegin(), a->data->shape.rend());
+    TensorP od;
+    nkg_var* v = unary_node(a, os, a->data->dtype, od);
+    auto fw = std::make_shared<Transpose>();
+    fw->ctx = a->ctx;
+    fw->operand = a->data;
+    fw->data = od;
+    uint64_t id = push(v, fw);
+    if (a->diff()) {
+      v->grad = std::make_shared<Gradient>(a->ctx, os, od->dtype);
+      auto bw = std::make_shared<TransposeBackward>();
+      bw->ctx = a->ctx;
+      bw->gradient = v->grad;
+      bw->operand_grad = a->grad;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+
+int nkg_pad_mode(nkg_var* a, int nsp, const int64_t* padding, int mode, float value, nkg_var** out) {
+  return guard([&] {
+    if (!a || !out || !padding) fail(NK_ERR_INVALID_ARG, "pad: NULL");
+    const Shape& s = a->data->shape;
+    if (nsp < 1 || nsp > 3 || (int)s.size() != nsp + 2)
+      fail(NK_ERR_INVALID_ARG, "pad: expects a (N, C, ...) operand with %d sample dimensions", nsp);
+    if (mode < NK_PAD_CONSTANT || mode > NK_PAD_REPLICATIVE) fail(NK_ERR_INVALID_ARG, "pad: bad mode %d", mode);
+    Shape os = s;
+    for (int k = 0; k < nsp; ++k) {
+      if (padding[k] < 0) fail(NK_ERR_INVALID_ARG, "pad: padding must be >= 0");
+      if (mode == NK_PAD_REFLECTIVE && padding[k] > 0 && padding[k] >= s[2 + k])
+        fail(NK_ERR_INVALID_ARG, "pad: reflective padding %lld must be smaller than the dimension %lld",
+             (long long)padding[k], (long long)s[2 + k]);
+      os[2 + k] += 2 * padding[k];
+    }
+    TensorP od;
+    nkg_var* v = unary_node(a, os, a->data->dtype, od);
+    auto fw = std::make_shared<PadNd>();
+    fw->ctx = a->ctx;
+    fw->operand = a->data;
+    fw->data = od;
+    fw->nsp = nsp;
+    fw->mode = mode;
+    fw->value = value;
+    for (int k = 0; k < 3; ++k) fw->pad[k] = k < nsp ? padding[k] : 0;
+    uint64_t id = push(v, fw);
+    if (a->diff()) {
+      v->grad = std::make_shared<Gradient>(a->ctx, os, od->dtype);
+      auto bw = std::make_shared<PadNdBackward>();
+      bw->ctx = a->ctx;
+      bw->gradient = v->grad;
+      bw->operand_grad = a->grad;
+      bw->nsp = nsp;
+      for (int k = 0; k < 3; ++k) bw->pad[k] = fw->pad[k];
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+
+static int matvec_impl(nkg_var* mat, nkg_var* vec, bool vm, nkg_var** out) {
+  return guard([&] {
+    if (!mat || !vec || !out) fail(NK_ERR_INVALID_ARG, "mv: NULL");
+    require_same_dtype(mat, vec, vm ? "vm" : "mv");
+    const Shape &ms = mat->data->shape, &vs = vec->data->shape;
+    if (ms.size() != 2 || vs.size() != 1) fail(NK_ERR_INVALID_ARG, "%s: needs a matrix and a vector", vm ? "vm" : "mv");
+    const int64_t need = vm ? ms[0] : ms[1];
+    if (vs[0] != need)
+      fail(NK_ERR_INVALID_ARG, "%s: incompatible shapes (%lld, %lld) and (%lld)", vm ? "vm" : "mv", (long long)ms[0],
+           (long long)ms[1], (long long)vs[0]);
+    nkg_var* first = vm ? vec : mat;
+    nkg_var* second = vm ? mat : vec;
+    nkg_var* v = new_like(first);
+    merge(v, first, second);
+    Shape os{vm ? ms[1] : ms[0]};
+    v->data = std::make_shared<Tensor>(mat->ctx, os, mat->data->dtype);
+    auto fw = std::make_shared<MatVec>();
+    fw->ctx = mat->ctx;
+    fw->mat = mat->data;
+    fw->vec = vec->data;
+    fw->data = v->data;
+    fw->vm = vm;
+    uint64_t id = push(v, fw);
+    if (mat->diff() || vec->diff()) {
+      v->grad = std::make_shared<Gradient>(mat->ctx, os, mat->data->dtype);
+      auto bw = std::make_shared<MatVecBackward>();
+      bw->ctx = mat->ctx;
+      bw->gradient = v->grad;
+      bw->mat = mat->data;
+      bw->vec = vec->data;
+      bw->mat_grad = mat->grad;
+      bw->vec_grad = vec->grad;
+      bw->vm = vm;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+int nkg_mv(nkg_var* mat, nkg_var* vec, nkg_var** out) { return matvec_impl(mat, vec, false, out); }
+int nkg_vm(nkg_var* vec, nkg_var* mat, nkg_var** out) { return matvec_impl(mat, vec, true, out); }
+
+int nkg_vv(nkg_var* a, nkg_var* b, nkg_var** out) {
+  return guard([&] {
+    if (!a || !b || !out) fail(NK_ERR_INVALID_ARG, "vv: NULL");
+    require_same_dtype(a, b, "vv");
+    if (a->data->shape.size() != 1 || b->data->shape.size() != 1 || a->data->shape[0] != b->data->shape[0])
+      fail(NK_ERR_INVALID_ARG, "vv: needs two vectors of the same length");
+    nkg_var* v = new_like(a);
+    merge(v, a, b);
+    v->data = std::make_shared<Tensor>(a->ctx, Shape{}, NK_F32);
+    auto fw = std::make_shared<VecVec>();
+    fw->ctx = a->ctx;
+    fw->left = a->data;
+    fw->right = b->data;
+    fw->data = v->data;
+    uint64_t id = push(v, fw);
+    if (a->diff() || b->diff()) {
+      v->grad = std::make_shared<Gradient>(a->ctx, Shape{}, NK_F32);
+      auto bw = std::make_shared<VecVecBackward>();
+      bw->ctx = a->ctx;
+      bw->gradient = v->grad;
+      bw->left = a->data;
+      bw->right = b->data;
+      bw->left_grad = a->grad;
+      bw->right_grad = b->grad;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+
+int nkg_convolution_nd(nkg_var* kernel, nkg_var* input, int nsp, const int64_t* stride, const int64_t* dilation,
+                       int64_t groups, nkg_var** out) {
+  return guard([&] {
+    if (!kernel || !input || !out || !stride || !dilation) fail(NK_ERR_INVALID_ARG, "convolution: NULL");
+    if (nsp == 2)
+      fail(NK_ERR_INVALID_ARG, "convolution: use nkg_convolution for 2d operands");
+    require_same_dtype(kernel, input, "convolution");
+    const Shape &ks = kernel->data->shape, &is = input->data->shape;
+    if (nsp < 1 || nsp > 3 || (int)is.size() != nsp + 2) fail(NK_ERR_INVALID_ARG, "convolution: input rank does not match %dd conv", nsp);
+    if (ks.size() != is.size()) fail(NK_ERR_INVALID_ARG, "Invalid kernel shape for %dd conv", nsp);
+    if (groups < 1) fail(NK_ERR_INVALID_ARG, "Invalid groups for %dd conv.", nsp);
+    ConvNdArgs a;
+    a.nsp = nsp, a.n = is[0], a.cin = is[1], a.cout = ks[0], a.groups = groups;
+    Shape os{is[0], ks[0]};
+    for (int k = 0; k < 3; ++k) a.in[k] = a.k[k] = a.s[k] = a.d[k] = 1;
+    for (int k = 0; k < nsp; ++k) {
+      if (stride[k] < 1 || dilation[k] < 1) fail(NK_ERR_INVALID_ARG, "Invalid stride/dilation for %dd conv.", nsp);
+      if (is[2 + k] < (ks[2 + k] - 1) * dilation[k] + 1)
+        fail(NK_ERR_INVALID_ARG, "The kernel size can't be greater than actual input size.");
+      a.in[k] = is[2 + k], a.k[k] = ks[2 + k], a.s[k] = stride[k], a.d[k] = dilation[k];
+      os.push_back((is[2 + k] - dilation[k] * (ks[2 + k] - 1) - 1) / stride[k] + 1);
+    }
+    if (is[1] % groups) fail(NK_ERR_INVALID_ARG, "In channels %lld is not divisible by groups %lld", (long long)is[1], (long long)groups);
+    if (ks[0] % groups) fail(NK_ERR_INVALID_ARG, "Out channels %lld is not divisible by groups %lld", (long long)ks[0], (long long)groups);
+    if (ks[1] * groups != is[1]) fail(NK_ERR_INVALID_ARG, "convolution: kernel in-channels %lld x groups %lld != input channels %lld", (long long)ks[1], (long long)groups, (long long)is[1]);
+    nkg_var* v = new_like(kernel);
+    merge(v, kernel, input);
+    v->data = std::make_shared<Tensor>(kernel->ctx, os, input->data->dtype);
+    auto fw = std::make_shared<ConvolutionNd>();
+    fw->ctx = kernel->ctx;
+    fw->input = input->data;
+    fw->kernel = kernel->data;
+    fw->data = v->data;
+    fw->a = a;
+    uint64_t id = push(v, fw);
+    if (kernel->diff() || input->diff()) {
+      v->grad = std::make_shared<Gradient>(kernel->ctx, os, input->data->dtype);
+      auto bw = std::make_shared<ConvolutionNdBackward>();
+      bw->ctx = kernel->ctx;
+      bw->gradient = v->grad;
+      bw->input = input->data;
+      bw->kernel = kernel->data;
+      bw->input_grad = input->grad;
+      bw->kernel_grad = kernel->grad;
+      bw->a = a;
+      push_bwd(v, id, bw);
+    }
+    *out = v;
+  });
+}
+
+// ---------------------------------------------------------------- optimizers on a leaf (neuronika-optim)
+int nkg_adam_step(nkg_var* p, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, float* master, int64_t step,
+                  float lr, float beta1, float beta2, float eps, float l1, float l2, float grad_scale) {
+  return guard([&] {
+    if (!p || !p->diff()) fail(NK_ERR_INVALID_ARG, "adam: parameter is not differentiable");
+    Gradient* g = p->grad->root();
+    ck(p->ctx, nk_adam_step(p->ctx, p->data->rptr(), p->data->dtype, p->grad->get(), g->dtype, exp_avg, exp_avg_sq,
+                            max_exp_avg_sq, master, size_t(p->data->n()), step, lr, beta1, beta2, eps, l1, l2, grad_scale, 1));
+    g->is_zero = false;
+  });
+}
+int nkg_rmsprop_step(nkg_var* p, float* square_avg, float* grad_avg, float* momentum_buf, float* master, float lr,
+                     float alpha, float eps, float momentum, float l1, float l2, float grad_scale) {
+  return guard([&] {
+    if (!p || !p->diff()) fail(NK_ERR_INVALID_ARG, "rmsprop: parameter is not differentiable");
+    Gradient* g = p->grad->root();
+    ck(p->ctx, nk_rmsprop_step(p->ctx, p->data->rptr(), p->data->dtype, p->grad->get(), g->dtype, square_avg, grad_avg,
+                               momentum_buf, master, size_t(p->data->n()), lr, alpha, eps, momentum, l1, l2, grad_scale, 1));
+    g->is_zero = false;
+  });
+}
+int nkg_adagrad_step(nkg_var* p, float* grad_sq, float* master, int64_t step, float lr, float lr_decay, float eps,
+                     float l1, float l2, float grad_scale) {
+  return guard([&] {
+    if (!p || !p->diff()) fail(NK_ERR_INVALID_ARG, "adagrad: parameter is not differentiable");
+    Gradient* g = p->grad->root();
+    ck(p->ctx, nk_adagrad_step(p->ctx, p->data->rptr(), p->data->dtype, p->grad->get(), g->dtype, grad_sq, master,
+                               size_t(p->data->n()), step, lr, lr_decay, eps, l1, l2, grad_scale, 1));
+    g->is_zero = false;
   });
 }
 

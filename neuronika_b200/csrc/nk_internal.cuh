@@ -28,6 +28,9 @@ struct nk_ctx {
   // stored to rs_dst[o] (rank o's slot buffer, peer-mapped, already offset to this rank's slot) instead of C
   int rs_world = 0, rs_rank = 0;
   void* rs_dst[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // NCCL communicator owned by the context (nk_comm.cu; libnccl is bound at run time)
+  void* comm = nullptr;
+  int comm_world = 0, comm_rank = 0;
 };
 
 int nk_set_error(nk_ctx* ctx, int code, const char* fmt, ...);

@@ -125,14 +125,15 @@ def mse_bwd(dx, x, t, g: CuArray, mean=True, beta=1.0):
 def nll(logp: CuArray, target: CuArray, mean=True, out=None) -> CuArray:
     out = out or CuArray(logp.device, (), F32)
     n, c = logp.shape
-    _ck(lib.nk_nll_fwd(logp.device.ctx, out.ptr, logp.ptr, target.ptr, n, c, logp.dtype, int(mean)), logp.device)
+    _ck(lib.nk_nll_fwd(logp.device.ctx, out.ptr, logp.ptr, target.ptr, target.dtype, n, c, logp.dtype, int(mean)),
+        logp.device)
     return out
 
 
 def nll_bwd(dlogp, target, g, mean=True, beta=1.0):
     n, c = dlogp.shape
-    _ck(lib.nk_nll_bwd(dlogp.device.ctx, dlogp.ptr, target.ptr, g.ptr, n, c, dlogp.dtype, int(mean), float(beta)),
-        dlogp.device)
+    _ck(lib.nk_nll_bwd(dlogp.device.ctx, dlogp.ptr, target.ptr, target.dtype, g.ptr, n, c, dlogp.dtype, int(mean),
+                       float(beta)), dlogp.device)
     return dlogp
 
 
@@ -222,3 +223,116 @@ def sgd_step(w: CuArray, g: CuArray, lr, l2=0.0, momentum=0.0, dampening=0.0, ne
                         master.ptr if master is not None else None, w.size, float(lr), float(l2), float(momentum),
                         float(dampening), int(nesterov), float(grad_scale), int(write_back_grad)), dev)
     return w
+
+
+# ---------------------------------------------------------------- 8-f: elementwise family
+BIN = {"add": L.NK_BIN_ADD, "sub": L.NK_BIN_SUB, "mul": L.NK_BIN_MUL, "div": L.NK_BIN_DIV}
+UN = {"neg": L.NK_UN_NEG, "exp": L.NK_UN_EXP, "ln": L.NK_UN_LN, "sqrt": L.NK_UN_SQRT, "sigmoid": L.NK_UN_SIGMOID,
+      "tanh": L.NK_UN_TANH, "softplus": L.NK_UN_SOFTPLUS, "leaky_relu": L.NK_UN_LEAKY_RELU, "powi": L.NK_UN_POWI}
+PAD = {"constant": L.NK_PAD_CONSTANT, "reflective": L.NK_PAD_REFLECTIVE, "replicative": L.NK_PAD_REPLICATIVE}
+
+
+def binary(op: str, l: CuArray, r: CuArray, out: CuArray | None = None) -> CuArray:
+    dev = l.device
+    shape = cobroadcast(l.shape, r.shape)
+    out = out or CuArray(dev, shape, l.dtype)
+    _ck(lib.nk_binary_bcast_fwd(dev.ctx, BIN[op], out.ptr, l.ptr, r.ptr, l.dtype, len(shape), L.shape_arr(shape),
+                                l.ndim, L.shape_arr(l.shape), r.ndim, L.shape_arr(r.shape)), dev)
+    return out
+
+
+def binary_bwd(op: str, side: int, dst: CuArray, g: CuArray, l: CuArray, r: CuArray, beta=1.0) -> CuArray:
+    """dst (the gradient of operand `side`) = beta*dst + unbroadcast(factor(g, l, r))."""
+    dev = g.device
+    _ck(lib.nk_binary_bcast_bwd(dev.ctx, BIN[op], int(side), dst.ptr, dst.dtype, g.ptr, l.ptr, r.ptr, g.dtype,
+                                l.ndim, L.shape_arr(l.shape), r.ndim, L.shape_arr(r.shape), float(beta)), dev)
+    return dst
+
+
+def unary(op: str, x: CuArray, iparam: int = 0, out: CuArray | None = None) -> CuArray:
+    out = out or CuArray(x.device, x.shape, x.dtype)
+    _ck(lib.nk_unary_fwd(x.device.ctx, UN[op], out.ptr, x.ptr, x.size, x.dtype, int(iparam)), x.device)
+    return out
+
+
+def unary_bwd(op: str, dx: CuArray, saved: CuArray | None, g: CuArray, iparam: int = 0, beta=1.0) -> CuArray:
+    _ck(lib.nk_unary_bwd(g.device.ctx, UN[op], dx.ptr, saved.ptr if saved is not None else None, g.ptr, g.size,
+                         g.dtype, int(iparam), float(beta)), g.device)
+    return dx
+
+
+def transpose(src: CuArray, out: CuArray | None = None, beta=0.0) -> CuArray:
+    out = out or CuArray(src.device, tuple(reversed(src.shape)), src.dtype)
+    _ck(lib.nk_transpose(src.device.ctx, out.ptr, out.dtype, src.ptr, src.dtype, src.ndim, L.shape_arr(src.shape),
+                         float(beta)), src.device)
+    return out
+
+
+def pad_nd(x: CuArray, padding, mode="constant", value=0.0, out=None) -> CuArray:
+    nsp = len(padding)
+    lead, sp = x.shape[:x.ndim - nsp], x.shape[x.ndim - nsp:]
+    out = out or CuArray(x.device, tuple(lead) + tuple(s + 2 * p for s, p in zip(sp, padding)), x.dtype)
+    planes = int(np.prod(lead)) if lead else 1
+    _ck(lib.nk_padnd_fwd(x.device.ctx, out.ptr, x.ptr, planes, nsp, L.shape_arr(sp), L.shape_arr(padding), PAD[mode],
+                         float(value), x.dtype), x.device)
+    return out
+
+
+def pad_nd_bwd(dx: CuArray, g: CuArray, padding, beta=1.0) -> CuArray:
+    nsp = len(padding)
+    lead, sp = dx.shape[:dx.ndim - nsp], dx.shape[dx.ndim - nsp:]
+    planes = int(np.prod(lead)) if lead else 1
+    _ck(lib.nk_padnd_bwd(dx.device.ctx, dx.ptr, g.ptr, planes, nsp, L.shape_arr(sp), L.shape_arr(padding), dx.dtype,
+                         float(beta)), dx.device)
+    return dx
+
+
+# ---------------------------------------------------------------- 8-f: mv / vm / vv
+def gemv(a: CuArray, x: CuArray, y: CuArray | None = None, trans=False, beta=0.0) -> CuArray:
+    rows, cols = a.shape
+    y = y or CuArray(a.device, (cols if trans else rows,), a.dtype)
+    _ck(lib.nk_gemv(a.device.ctx, int(trans), rows, cols, a.ptr, x.ptr, float(beta), y.ptr, a.dtype, y.dtype), a.device)
+    return y
+
+
+def outer_acc(a: CuArray, u: CuArray, v: CuArray, beta=1.0) -> CuArray:
+    rows, cols = a.shape
+    _ck(lib.nk_outer_acc(a.device.ctx, a.ptr, a.dtype, u.ptr, v.ptr, rows, cols, u.dtype, float(beta)), a.device)
+    return a
+
+
+def dot(a: CuArray, b: CuArray, out: CuArray | None = None) -> CuArray:
+    out = out or CuArray(a.device, (), F32)
+    _ck(lib.nk_dot(a.device.ctx, out.ptr, a.ptr, b.ptr, a.size, a.dtype), a.device)
+    return out
+
+
+def scale_acc(dst: CuArray, x: CuArray, scalar: CuArray, beta=1.0) -> CuArray:
+    _ck(lib.nk_scale_acc(dst.device.ctx, dst.ptr, dst.dtype, x.ptr, x.dtype, scalar.ptr, x.size, float(beta)), dst.device)
+    return dst
+
+
+# ---------------------------------------------------------------- 8-f: 1-d / 3-d convolution
+def _convnd_args(x_shape, w_shape, stride, dilation, groups):
+    nsp = len(x_shape) - 2
+    return [nsp, x_shape[0], x_shape[1], L.shape_arr(x_shape[2:]), w_shape[0], L.shape_arr(w_shape[2:]),
+            L.shape_arr(stride), L.shape_arr(dilation), groups]
+
+
+def convnd(x: CuArray, w: CuArray, stride, dilation, groups=1, out=None) -> CuArray:
+    out = out or CuArray(x.device, conv_out_shape(x.shape, w.shape, stride, dilation), x.dtype)
+    _ck(lib.nk_convnd_fwd(x.device.ctx, out.ptr, x.ptr, w.ptr, *_convnd_args(x.shape, w.shape, stride, dilation, groups),
+                          x.dtype), x.device)
+    return out
+
+
+def convnd_bwd_input(dx: CuArray, g: CuArray, w: CuArray, stride, dilation, groups=1, beta=1.0) -> CuArray:
+    _ck(lib.nk_convnd_bwd_input(g.device.ctx, dx.ptr, g.ptr, w.ptr,
+                                *_convnd_args(dx.shape, w.shape, stride, dilation, groups), g.dtype, float(beta)), g.device)
+    return dx
+
+
+def convnd_bwd_kernel(dw: CuArray, g: CuArray, x: CuArray, stride, dilation, groups=1, beta=1.0) -> CuArray:
+    _ck(lib.nk_convnd_bwd_kernel(g.device.ctx, dw.ptr, dw.dtype, g.ptr, x.ptr,
+                                 *_convnd_args(x.shape, dw.shape, stride, dilation, groups), g.dtype, float(beta)), g.device)
+    return dw

@@ -248,7 +248,9 @@ def rs_eligible(shape, world: int, min_elems: int = 1 << 20) -> bool:
     if len(shape) != 2 or world < 2:
         return False
     rows, cols = int(shape[0]), int(shape[1])
-    return rows % (world * 128) == 0 and rows * cols >= min_elems and (rows // world * cols) % 4 == 0
+    # nk_gemm_rs runs the 128x256 tcgen05 tile only (cols > 128) on TMA-addressable operands (cols % 8 == 0)
+    return (rows % (world * 128) == 0 and rows * cols >= min_elems and (rows // world * cols) % 4 == 0
+            and cols > 128 and cols % 8 == 0)
 
 
 class FusedGradientExchange:

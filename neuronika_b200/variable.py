@@ -54,6 +54,28 @@ _G = {
     "nkg_convolution": (i32, [vp, vp, i64, i64, i64, i64, i64, pvp]),
     "nkg_flatten": (i32, [vp, pvp]),
     "nkg_sgd_step": (i32, [vp, vp, vp, f32, f32, f32, f32, i32, f32]),
+    "nkg_sub": (i32, [vp, vp, pvp]),
+    "nkg_mul": (i32, [vp, vp, pvp]),
+    "nkg_div": (i32, [vp, vp, pvp]),
+    "nkg_unary": (i32, [vp, i32, i32, pvp]),
+    "nkg_neg": (i32, [vp, pvp]),
+    "nkg_exp": (i32, [vp, pvp]),
+    "nkg_ln": (i32, [vp, pvp]),
+    "nkg_sqrt": (i32, [vp, pvp]),
+    "nkg_sigmoid": (i32, [vp, pvp]),
+    "nkg_tanh": (i32, [vp, pvp]),
+    "nkg_softplus": (i32, [vp, pvp]),
+    "nkg_leaky_relu": (i32, [vp, pvp]),
+    "nkg_pow": (i32, [vp, i32, pvp]),
+    "nkg_transpose": (i32, [vp, pvp]),
+    "nkg_pad_mode": (i32, [vp, i32, pi64, i32, f32, pvp]),
+    "nkg_mv": (i32, [vp, vp, pvp]),
+    "nkg_vm": (i32, [vp, vp, pvp]),
+    "nkg_vv": (i32, [vp, vp, pvp]),
+    "nkg_convolution_nd": (i32, [vp, vp, i32, pi64, pi64, i64, pvp]),
+    "nkg_adam_step": (i32, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, f32]),
+    "nkg_rmsprop_step": (i32, [vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, f32]),
+    "nkg_adagrad_step": (i32, [vp, vp, vp, i64, f32, f32, f32, f32, f32, f32]),
     "nkg_set_grad_hook": (i32, [vp, vp, vp, i32]),
     "nkg_set_grad_rs": (i32, [vp, i32, i32, pvp, vp, vp]),
 }
@@ -170,6 +192,22 @@ class Var:
     def mm(self, other): return self._binary(lib.nkg_mm, other)                   # MatMatMul, core lib.rs:4-13
     def mm_t(self, other): return self._binary(lib.nkg_mm_t, other)               # MatMatMulT, core lib.rs:19-28
     def __add__(self, other): return self._binary(lib.nkg_add, other)
+    def __sub__(self, other): return self._binary(lib.nkg_sub, other)             # subtraction/mod.rs
+    def __mul__(self, other): return self._binary(lib.nkg_mul, other)             # multiplication/mod.rs
+    def __truediv__(self, other): return self._binary(lib.nkg_div, other)         # division/mod.rs
+    def __neg__(self): return self._unary(lib.nkg_neg)                            # negation/mod.rs
+    def exp(self): return self._unary(lib.nkg_exp)
+    def ln(self): return self._unary(lib.nkg_ln)
+    def sqrt(self): return self._unary(lib.nkg_sqrt)
+    def sigmoid(self): return self._unary(lib.nkg_sigmoid)
+    def tanh(self): return self._unary(lib.nkg_tanh)
+    def softplus(self): return self._unary(lib.nkg_softplus)
+    def leaky_relu(self): return self._unary(lib.nkg_leaky_relu)
+    def pow(self, exp: int): return self._unary(lib.nkg_pow, int(exp))            # power/mod.rs (`powi`)
+    def t(self): return self._unary(lib.nkg_transpose)                            # transpose/mod.rs (reverses all axes)
+    def mv(self, vector): return self._binary(lib.nkg_mv, vector)                 # MatVecMul, core lib.rs
+    def vm(self, matrix): return self._binary(lib.nkg_vm, matrix)                 # VecMatMul
+    def vv(self, other): return self._binary(lib.nkg_vv, other)                   # VecVecMul
     def relu(self): return self._unary(lib.nkg_relu)
     def softmax(self, axis: int): return self._unary(lib.nkg_softmax, int(axis))
     def log_softmax(self, axis: int): return self._unary(lib.nkg_log_softmax, int(axis))
@@ -179,18 +217,29 @@ class Var:
     def nll_loss(self, target, reduction=Reduction.Mean): return self._binary(lib.nkg_nll_loss, target, int(reduction))
     def flatten(self): return self._unary(lib.nkg_flatten)
 
-    def pad(self, padding, value: float = 0.0):
-        """`pad(padding, mode)` with Zero / Constant(value) modes (var.rs:726-737)."""
-        ph, pw = padding
-        return self._unary(lib.nkg_pad, int(ph), int(pw), float(value))
+    def pad(self, padding, value: float = 0.0, mode: str = "constant"):
+        """`pad(padding, mode)` (var.rs:726-737): Zero / Constant(value) / Reflective / Replicative over the 1..3
+        sample dimensions of a (N, C, ...) operand."""
+        modes = {"constant": L.NK_PAD_CONSTANT, "zero": L.NK_PAD_CONSTANT, "reflective": L.NK_PAD_REFLECTIVE,
+                 "replicative": L.NK_PAD_REPLICATIVE}
+        if mode not in modes:
+            raise L.NkError(-1, f"unknown padding mode {mode!r}")
+        padding = tuple(int(p) for p in padding)
+        if len(padding) == 2 and modes[mode] == L.NK_PAD_CONSTANT:
+            return self._unary(lib.nkg_pad, padding[0], padding[1], float(value))
+        return self._unary(lib.nkg_pad_mode, len(padding), L.shape_arr(padding), modes[mode], float(value))
 
     def convolution(self, input, stride=(1, 1), dilation=(1, 1), groups: int = 1):
         """`kernel.convolution(input, stride, dilation, groups)` -- the receiver is the kernel
         (Convolution trait, core lib.rs:91-106; var.rs:704-716)."""
-        if len(stride) != 2:
-            raise L.NkError(-1, f"Invalid stride {list(stride)} for 2d conv.")
-        if len(dilation) != 2:
-            raise L.NkError(-1, f"Invalid dilation {list(dilation)} for 2d conv.")
+        nsp = len(self.shape) - 2
+        if len(stride) != nsp:
+            raise L.NkError(-1, f"Invalid stride {list(stride)} for {nsp}d conv.")
+        if len(dilation) != nsp:
+            raise L.NkError(-1, f"Invalid dilation {list(dilation)} for {nsp}d conv.")
+        if nsp != 2:       # 1-d / 3-d operands (convolution/mod.rs is generic over the sample dimensions)
+            return self._binary(lib.nkg_convolution_nd, input, nsp, L.shape_arr(stride), L.shape_arr(dilation),
+                                int(groups))
         return self._binary(lib.nkg_convolution, input, int(stride[0]), int(stride[1]), int(dilation[0]),
                             int(dilation[1]), int(groups))
 

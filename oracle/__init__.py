@@ -19,3 +19,4 @@ implements the intended mathematics, which coincides with every enabled
 reference test and with torch CPU autograd.
 """
 from .nodes import *  # noqa: F401,F403
+from .nodes_next import *  # noqa: F401,F403

@@ -11,6 +11,7 @@ computed in this script: every number is lifted verbatim from the reference's
 Outputs (committed):
   tests/golden/conv.json      -- conv{1,2,3}d plain/strided/dilated/grouped + im2col layout
   tests/golden/tensors.json   -- per test-fn ordered tensor literals of the node tests
+  tests/golden/tensors_next.json -- the same for the SURVEY.md 8-f nodes (unary family, transpose, mv / vm / vv)
 """
 from __future__ import annotations
 
@@ -115,8 +116,14 @@ TENSOR_CALL = re.compile(
     flags=re.S)
 
 
-def gen_tensors():
-    files = [
+NEXT_FILES = [   # SURVEY.md 8-f nodes whose (disabled, old-API) tests hold literal vectors
+    "negation", "transpose", "power", "sqrt", "sigmoid", "tanh", "softplus", "leaky_relu",
+    "matrix_vector_mul", "vector_matrix_mul", "vector_vector_mul",
+]
+
+
+def gen_tensors(files=None):
+    files = files or [
         "matrix_matrix_mul", "matrix_matrix_mul_t", "relu", "softmax", "logsoftmax",
         "squared_error", "nll", "sum", "mean", "addition", "pad/zero", "pad/constant",
     ]
@@ -155,6 +162,10 @@ def main():
     tensors = gen_tensors()
     with open(os.path.join(HERE, "tensors.json"), "w") as fh:
         json.dump(tensors, fh, indent=0, separators=(",", ":"))
+    nxt = gen_tensors(NEXT_FILES)
+    with open(os.path.join(HERE, "tensors_next.json"), "w") as fh:
+        json.dump(nxt, fh, indent=0, separators=(",", ":"))
+    tensors = dict(tensors, **nxt)
     print("conv cases:", sorted(conv))
     for f, d in tensors.items():
         print(f, {k: [len(b["tensors"]) for b in v] for k, v in d.items()})
