@@ -79,6 +79,22 @@ int nk_host_alloc(nk_ctx* ctx, size_t bytes, void** hptr);           /* pinned h
 int nk_host_free(nk_ctx* ctx, void* hptr);
 int nk_fill(nk_ctx* ctx, void* dptr, int dtype, size_t n, float value);
 int nk_cast(nk_ctx* ctx, void* dst, int dst_dtype, const void* src, int src_dtype, size_t n);
+/* ---- whole-step capture.  A training step launches the same kernels every iteration (the reference rebuilds the
+ * same define-by-run graph each time, examples/quickstart.rs:216-227), so the step can be recorded once and replayed
+ * with one driver call: between nk_capture_begin and nk_capture_end every kernel / copy / memset this library
+ * enqueues on the context stream -- and on streams that join it through events, e.g. the exchange side stream -- is
+ * recorded into a CUDA graph instead of running.  While capturing, nk_alloc / nk_alloc_uninit take memory from an
+ * arena of `arena_bytes` owned by the graph (fixed addresses on every replay; blocks freed inside the capture are
+ * recycled) and nk_free of arena memory is a no-op for as long as the graph lives.  Things that cannot be captured
+ * (nk_d2h, nk_sync, growth of the scratch workspace) fail: run the step once eagerly first.  nk_graph_launch replays
+ * the step on the context stream; results are in the same buffers every time. */
+typedef struct nk_graph nk_graph;
+int nk_capture_begin(nk_ctx* ctx, size_t arena_bytes);
+int nk_capture_end(nk_ctx* ctx, nk_graph** out);
+int nk_graph_launch(nk_ctx* ctx, nk_graph* graph);
+int nk_graph_destroy(nk_ctx* ctx, nk_graph* graph);
+int64_t nk_graph_kernel_count(nk_graph* graph);   /* kernel nodes per replay (counted into nk_launch_count) */
+size_t nk_graph_arena_used(nk_graph* graph);
 /* CUDA-event stopwatch on the context stream */
 int nk_timer_start(nk_ctx* ctx);
 int nk_timer_stop(nk_ctx* ctx, float* ms);
@@ -309,6 +325,18 @@ int nk_gemm_rs(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_
                int rank, int ab_dtype);
 int nk_reduce_bcast(nk_ctx* ctx, const float* slots, void* const* grads, int world, int rank,
                     int64_t shard_elems, int max_ctas);
+/* barrier -> owner reduce + broadcast -> barrier as ONE kernel whose epoch lives on the device (`state`: 16 bytes of
+ * zero-initialised LOCAL device memory per exchange sequence), so the launch is identical every step and can be
+ * captured in a CUDA graph.  flags[r] = rank r's flag words (>= 2*world, zero-initialised, peer-mapped).  Work is
+ * handed out in 32 KB chunks, so max_ctas may be the SM count (0 = that): CTAs that do not fit beside a running
+ * GEMM start when it retires.  All ranks must issue the same sequence of calls on the same (flags, state). */
+int nk_reduce_exchange(nk_ctx* ctx, const float* slots, void* const* grads, void* const* flags, int world,
+                       int rank, int64_t shard_elems, void* state, int max_ctas);
+/* all-reduce (sum, rank order: bit-identical on every replica) of a small local vector `grad` (n <= 2^20 floats: biases,
+ * the 10-wide layer) through peer memory in one single-CTA kernel: slots[r] = rank r's receive buffer (world*n floats),
+ * flags / state as above but separate from nk_reduce_exchange's. */
+int nk_peer_allreduce_small(nk_ctx* ctx, float* grad, void* const* slots, void* const* flags, int world, int rank,
+                            int64_t n, void* state);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,12 @@ _PROTOS = {
     "nk_host_free": (i32, [vp, vp]),
     "nk_fill": (i32, [vp, vp, i32, sz, f32]),
     "nk_cast": (i32, [vp, vp, i32, vp, i32, sz]),
+    "nk_capture_begin": (i32, [vp, sz]),
+    "nk_capture_end": (i32, [vp, C.POINTER(vp)]),
+    "nk_graph_launch": (i32, [vp, vp]),
+    "nk_graph_destroy": (i32, [vp, vp]),
+    "nk_graph_kernel_count": (i64, [vp]),
+    "nk_graph_arena_used": (sz, [vp]),
     "nk_timer_start": (i32, [vp]),
     "nk_timer_stop": (i32, [vp, C.POINTER(f32)]),
     "nk_gemm": (i32, [vp, i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, i32, i32]),
@@ -101,6 +107,8 @@ _PROTOS = {
     "nk_peer_barrier": (i32, [vp, pvp, i32, i32, C.c_uint32]),
     "nk_gemm_rs": (i32, [vp, i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, pvp, i32, i32, i32]),
     "nk_reduce_bcast": (i32, [vp, vp, pvp, i32, i32, i64, i32]),
+    "nk_reduce_exchange": (i32, [vp, vp, pvp, pvp, i32, i32, i64, vp, i32]),
+    "nk_peer_allreduce_small": (i32, [vp, vp, pvp, pvp, i32, i32, i64, vp]),
     "nk_binary_bcast_fwd": (i32, [vp, i32, vp, vp, vp, i32, i32, pi64, i32, pi64, i32, pi64]),
     "nk_binary_bcast_bwd": (i32, [vp, i32, i32, vp, i32, vp, vp, vp, i32, i32, pi64, i32, pi64, f32]),
     "nk_unary_fwd": (i32, [vp, i32, vp, vp, sz, i32, i32]),

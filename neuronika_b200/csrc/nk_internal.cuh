@@ -5,9 +5,21 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
 #include <string>
+#include <vector>
 
 #include "nk_b200.h"
+
+// a captured step (nk_capture_begin / nk_capture_end): the instantiated CUDA graph plus the arena its buffers live in
+struct nk_graph {
+  nk_ctx* ctx = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  char* arena = nullptr;
+  size_t arena_bytes = 0, arena_used = 0;
+  uint64_t kernel_nodes = 0;
+};
 
 struct nk_ctx {
   int device = 0;
@@ -28,6 +40,14 @@ struct nk_ctx {
   // stored to rs_dst[o] (rank o's slot buffer, peer-mapped, already offset to this rank's slot) instead of C
   int rs_world = 0, rs_rank = 0;
   void* rs_dst[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // stream capture of a whole step (nk_ctx.cu): while capturing, nk_alloc* hand out memory from the graph's arena
+  // (fixed addresses for every replay, freed blocks are recycled within the capture) and nk_free of an arena pointer
+  // is a no-op, during the capture and for as long as the graph lives
+  nk_graph* capturing = nullptr;
+  std::multimap<size_t, void*> arena_free;      // (rounded size -> block) freed during the running capture
+  std::map<void*, size_t> capturing_sizes;      // rounded size of every block handed out by the running capture
+  std::vector<nk_graph*> graphs;
+  std::vector<void*> deferred_frees;            // pool memory released while capturing: freed for real at capture end
   // NCCL communicator owned by the context (nk_comm.cu; libnccl is bound at run time)
   void* comm = nullptr;
   int comm_world = 0, comm_rank = 0;

@@ -79,9 +79,176 @@ __global__ void __launch_bounds__(1024) reduce_bcast_kernel(const float4* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// One kernel for "barrier -> owner reduce + broadcast -> barrier", with the epoch kept on the device so that the launch
+// is identical every step (capturable in a CUDA graph) and with the work handed out dynamically, so that it may be
+// launched with a CTA per SM: the CTAs that find an SM free while a GEMM runs start at once, the others pick up
+// whatever is left when the GEMM's CTAs retire.
+//   phase A  every rank tells every peer "my pushes into your slots have landed" (the GEMM that pushed them precedes
+//            this kernel in stream order) and waits for the same word from all peers;
+//   phase B  32 KB chunks of the local slot buffers are summed in rank order and stored into every replica's gradient;
+//   phase C  the last CTA to finish tells every peer "my sums have landed in your gradient" and waits for theirs, so
+//            the kernel's completion means this replica's gradient is final.
+struct ExState {
+  uint32_t epoch, done, next_chunk, error;
+};
+constexpr long long kPeerTimeout = 60000000000LL;  // ~30 s of SM clocks: a peer died; fail loudly instead of hanging
+
+__device__ __forceinline__ void peer_signal(void* flag_base, int index, uint32_t epoch) {
+  uint32_t* p = static_cast<uint32_t*>(flag_base) + index;
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void peer_wait(const void* flag_base, int index, uint32_t epoch, ExState* st) {
+  const uint32_t* p = static_cast<const uint32_t*>(flag_base) + index;
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (int32_t(v - epoch) >= 0) break;
+    if (clock64() - t0 > kPeerTimeout) {
+      st->error = 1;
+      __trap();
+    }
+    __nanosleep(32);
+  }
+}
+
+constexpr int kExThreads = 512;
+constexpr int kExChunkVec = 2048;  // float4 per chunk and slot (32 KB)
+
+__global__ void __launch_bounds__(kExThreads) reduce_exchange_kernel(const float4* __restrict__ slots, PeerPtrs grads,
+                                                                     PeerPtrs flags, int world, int rank,
+                                                                     int64_t shard_vec, int64_t offset_vec, ExState* st) {
+  __shared__ uint32_t s_epoch;
+  __shared__ uint32_t s_chunk;
+  __shared__ int s_last;
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(&st->epoch) + 1u;
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  // ---- phase A
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    peer_signal(flags.p[threadIdx.x], rank, epoch);
+  }
+  if (threadIdx.x < world) peer_wait(flags.p[rank], threadIdx.x, epoch, st);
+  __syncthreads();
+  // ---- phase B
+  const int64_t chunks = (shard_vec + kExChunkVec - 1) / kExChunkVec;
+  for (;;) {
+    if (threadIdx.x == 0) s_chunk = atomicAdd(&st->next_chunk, 1u);
+    __syncthreads();
+    const int64_t c = s_chunk;
+    __syncthreads();
+    if (c >= chunks) break;
+    const int64_t base = c * kExChunkVec;
+#pragma unroll
+    for (int u = 0; u < kExChunkVec / kExThreads; ++u) {
+      const int64_t i = base + u * kExThreads + threadIdx.x;
+      if (i < shard_vec) {
+        float4 acc = __ldcs(slots + i);
+        for (int s = 1; s < world; ++s) {
+          const float4 v = __ldcs(slots + s * shard_vec + i);
+          acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+        }
+        for (int r = 0; r < world; ++r) {
+          const int rr = (r + rank) % world;  // every rank starts with a different replica: spreads the links
+          static_cast<float4*>(grads.p[rr])[offset_vec + i] = acc;
+        }
+      }
+    }
+  }
+  // ---- phase C
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&st->done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x < world) {
+      peer_signal(flags.p[threadIdx.x], world + rank, epoch);
+      peer_wait(flags.p[rank], world + threadIdx.x, epoch, st);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      st->done = 0;
+      st->next_chunk = 0;
+      __threadfence();
+      st->epoch = epoch;
+    }
+  }
+}
+
+// all-reduce of a SMALL vector (biases, the 10-wide layer) through peer memory, one CTA: every rank stores its local
+// values into slot `rank` of every peer, signals, waits for all peers, then sums the `world` slots it received in rank
+// order -- so every replica computes bit-identical sums -- into its own gradient.
+__global__ void __launch_bounds__(1024) small_allreduce_kernel(float* __restrict__ grad, PeerPtrs slots, PeerPtrs flags,
+                                                               int world, int rank, int64_t n, ExState* st) {
+  __shared__ uint32_t s_epoch;
+  if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(&st->epoch) + 1u;
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  for (int r = 0; r < world; ++r) {
+    float* dst = static_cast<float*>(slots.p[(r + rank) % world]) + int64_t(rank) * n;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = grad[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) {
+    peer_signal(flags.p[threadIdx.x], rank, epoch);
+    peer_wait(flags.p[rank], threadIdx.x, epoch, st);
+  }
+  __syncthreads();
+  const float* mine = static_cast<const float*>(slots.p[rank]);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float acc = __ldcv(mine + i);
+    for (int s = 1; s < world; ++s) acc += __ldcv(mine + int64_t(s) * n + i);
+    grad[i] = acc;
+  }
+  // second handshake: nobody may overwrite a slot (next step) before every rank has read it
+  __syncthreads();
+  if (threadIdx.x < world) {
+    peer_signal(flags.p[threadIdx.x], world + rank, epoch);
+    peer_wait(flags.p[rank], world + threadIdx.x, epoch, st);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) st->epoch = epoch;
+}
+
 }  // namespace
 
 extern "C" {
+
+int nk_reduce_exchange(nk_ctx* ctx, const float* slots, void* const* grads, void* const* flags, int world, int rank,
+                       int64_t shard_elems, void* state, int max_ctas) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, slots && grads && flags && state && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world,
+             "nk_reduce_exchange: bad arguments");
+  NK_REQUIRE(ctx, shard_elems > 0 && shard_elems % 4 == 0, "nk_reduce_exchange: shard of %lld elements is not a positive multiple of 4",
+             (long long)shard_elems);
+  PeerPtrs g, f;
+  for (int i = 0; i < kMaxWorld; ++i) g.p[i] = i < world ? grads[i] : nullptr, f.p[i] = i < world ? flags[i] : nullptr;
+  const int64_t vec = shard_elems / 4;
+  const int64_t chunks = (vec + kExChunkVec - 1) / kExChunkVec;
+  int grid = max_ctas > 0 ? max_ctas : ctx->sm_count;
+  if (grid > chunks) grid = int(chunks);
+  reduce_exchange_kernel<<<grid, kExThreads, 0, ctx->stream>>>(reinterpret_cast<const float4*>(slots), g, f, world, rank, vec,
+                                                               int64_t(rank) * vec, static_cast<ExState*>(state));
+  NK_LAUNCHED(ctx, "reduce_exchange");
+  return NK_OK;
+}
+
+int nk_peer_allreduce_small(nk_ctx* ctx, float* grad, void* const* slots, void* const* flags, int world, int rank,
+                            int64_t n, void* state) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, grad && slots && flags && state && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world,
+             "nk_peer_allreduce_small: bad arguments");
+  NK_REQUIRE(ctx, n > 0 && n <= (int64_t(1) << 20), "nk_peer_allreduce_small: n = %lld outside (0, 2^20]; use nk_allreduce_sum",
+             (long long)n);
+  PeerPtrs s, f;
+  for (int i = 0; i < kMaxWorld; ++i) s.p[i] = i < world ? slots[i] : nullptr, f.p[i] = i < world ? flags[i] : nullptr;
+  small_allreduce_kernel<<<1, 1024, 0, ctx->stream>>>(grad, s, f, world, rank, n, static_cast<ExState*>(state));
+  NK_LAUNCHED(ctx, "peer_allreduce_small");
+  return NK_OK;
+}
 
 int nk_ipc_alloc(nk_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return NK_ERR_INVALID_ARG;

@@ -75,6 +75,16 @@ class Device:
         L.check(L.lib.nk_timer_stop(self.ctx, C.byref(ms)), self.ctx)
         return float(ms.value)
 
+    def capture(self, arena_bytes: int = 1 << 30) -> "_Capture":
+        """Record everything the enclosed step launches into a CUDA graph (nk_capture_begin / nk_capture_end):
+
+            with dev.capture(arena_bytes) as cap:
+                step()                      # builds the tape, forward, backward, exchange, optimizer -- recorded, not run
+            cap.graph.launch()              # replays the whole step with one driver call
+
+        Run the step once eagerly first (first-use allocations cannot be captured)."""
+        return _Capture(self, int(arena_bytes))
+
     def close(self) -> None:
         if getattr(self, "ctx", None) is not None and self.ctx:
             L.lib.nk_ctx_destroy(self.ctx)
@@ -93,6 +103,46 @@ class Device:
         a = CuArray(self, np.shape(array), dtype)
         a.copy_from(array)
         return a
+
+
+class CapturedStep:
+    """An instantiated CUDA graph of one step plus the arena its intermediates live in (nk_graph)."""
+
+    def __init__(self, device: Device, handle):
+        self.device, self._h = device, handle
+
+    def launch(self) -> None:
+        L.check(L.lib.nk_graph_launch(self.device.ctx, self._h), self.device.ctx)
+
+    @property
+    def kernel_count(self) -> int:
+        return int(L.lib.nk_graph_kernel_count(self._h))
+
+    @property
+    def arena_used(self) -> int:
+        return int(L.lib.nk_graph_arena_used(self._h))
+
+    def close(self) -> None:
+        if self._h and self.device.ctx:
+            L.lib.nk_graph_destroy(self.device.ctx, self._h)
+        self._h = None
+
+
+class _Capture:
+    def __init__(self, device: Device, arena_bytes: int):
+        self.device, self.arena_bytes, self.graph = device, arena_bytes, None
+
+    def __enter__(self):
+        L.check(L.lib.nk_capture_begin(self.device.ctx, self.arena_bytes), self.device.ctx)
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        h = C.c_void_p()
+        rc = L.lib.nk_capture_end(self.device.ctx, C.byref(h))
+        if exc_type is None:
+            L.check(rc, self.device.ctx)
+            self.graph = CapturedStep(self.device, h)
+        return False
 
 
 class CuArray:

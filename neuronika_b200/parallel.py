@@ -254,23 +254,32 @@ def rs_eligible(shape, world: int, min_elems: int = 1 << 20) -> bool:
 
 
 class FusedGradientExchange:
-    """Data-parallel gradient exchange with the reduce-scatter fused into the dW GEMM (nk_gemm_rs) for the large
-    matrices, and the NCCL all-reduce for everything else (biases, small or oddly shaped matrices).
+    """Data-parallel gradient exchange over NVLink peer memory, no library collective on the path:
+
+      * large matrices: the reduce-scatter is fused into the dW GEMM epilogue (nk_gemm_rs), then ONE kernel per matrix on
+        a side stream does barrier -> owner reduce -> broadcast into every replica's bucket -> barrier
+        (nk_reduce_exchange, device-resident epoch);
+      * everything else (biases, small or oddly shaped matrices): one single-CTA kernel per contiguous bucket range
+        writes the local values into every peer's receive slots and sums the `world` copies in rank order
+        (nk_peer_allreduce_small); ranges above 2^20 elements go through the context-owned NCCL communicator
+        (nk_allreduce_sum).
+
+    Every launch is identical from step to step, so the whole step -- exchange included -- can be captured in a CUDA
+    graph (Device.capture).  Every replica receives bit-identical gradients.
 
         ex = FusedGradientExchange(device, compute_stream, shapes, world, rank)     # owns the gradient bucket
         params = [from_ndarray(...).requires_grad(F32, ex.bucket.views[i]) for i ...]
         ex.attach(params)
-        loss.backward(1.0)      # dW epilogues push shards to their owners; reduce + broadcast run on a side stream
+        loss.backward(1.0)      # dW epilogues push shards to their owners; the exchange kernels run on a side stream
         ex.wait()               # all gradients (summed over ranks) are in the bucket; then optimizer.step()
+    """
 
-    Per large matrix and step, on the side stream: barrier (all pushes landed) -> nk_reduce_bcast (the owner sums its
-    `world` slots in rank order and stores the sums into every replica's bucket) -> barrier (all sums landed).  Every
-    replica receives bit-identical gradients."""
+    SMALL_MAX = 1 << 20
 
-    def __init__(self, device, compute_stream, shapes, world: int, rank: int, reduce_ctas: int = 20,
+    def __init__(self, device, compute_stream, shapes, world: int, rank: int, reduce_ctas: int = 0,
                  min_elems: int = 1 << 20):
         import torch
-        from .device import F32
+        from .device import F32, CuArray
         self.torch, self.device, self.compute = torch, device, compute_stream
         self.world, self.rank, self.reduce_ctas = world, rank, reduce_ctas
         self.layout = BucketLayout(shapes)
@@ -283,23 +292,30 @@ class FusedGradientExchange:
             self.slot_off[i] = off
             off += int(np.prod(self.layout.shapes[i]))
         self.slots = PeerMemory(device, max(off, 4) * 4, world, rank)
-        self.flags = PeerMemory(device, 256, world, rank)
-        self.epoch = 0
+        # receive slots of the small all-reduce: world copies of every non-fused element
+        small_total = self.layout.total - off
+        self.small_slots = PeerMemory(device, max(small_total, 4) * 4 * world, world, rank)
+        self.flags = PeerMemory(device, 1024, world, rank)          # words [0,16): exchange, [64,80): small all-reduce
+        self.state = CuArray(device, (16,), F32)                    # zero-filled local words: ExState x 2
         self.comm = torch.cuda.Stream(device=device.index)
         self._events = [torch.cuda.Event() for _ in range(4 * len(shapes) + 8)]
         self._ev_i = 0
         self._pending = []
-        self.ranges = ReadyRanges(min_elems=1 << 62)      # everything that is not fused is all-reduced in bulk
+        self.ranges = ReadyRanges(min_elems=1 << 62)      # everything that is not fused is exchanged in bulk
         self.flat = self.bucket.as_torch()
         self.pushed = 0
         self.comm_device = None
+        self._params = []
+        self._nccl_ready = False
         import os
         self._debug_skip_reduce = bool(os.environ.get("NK_DP_DEBUG_SKIP_REDUCE"))
 
     def attach(self, params) -> None:
         from .device import Device
         # the side stream gets its own context handle bound to the same device: kernels are enqueued on self.comm
-        self.comm_device = Device(self.device.index, stream=self.comm.cuda_stream)
+        if self.comm_device is None:
+            self.comm_device = Device(self.device.index, stream=self.comm.cuda_stream)
+        self._params = list(params)
         lay = self.layout
         for pi, p in enumerate(params):
             if pi in self.fused:
@@ -307,14 +323,15 @@ class FusedGradientExchange:
                 p.set_grad_rs(self.world, self.rank, [int(v) for v in table],
                               lambda pushed, pi=pi: self._pushed(pi, pushed))
             else:
-                n = int(np.prod(lay.shapes[pi])) if lay.shapes[pi] else 1
                 p.set_grad_hook(lambda b, e, off=lay.offsets[pi]: self.ranges.add(off + b, off + e))
 
-    def _barrier(self) -> None:
-        from . import _lib as L
-        self.epoch += 1
-        L.check(L.lib.nk_peer_barrier(self.comm_device.ctx, self.flags.table, self.world, self.rank, self.epoch),
-                self.comm_device.ctx)
+    def detach(self) -> None:
+        """Remove the exchange plans and hooks from the parameters (gradients stay local afterwards)."""
+        for pi, p in enumerate(self._params):
+            if pi in self.fused:
+                p.set_grad_rs(0, 0, None, None)
+            else:
+                p.set_grad_hook(None)
 
     def _pushed(self, pi: int, pushed: int) -> None:
         # called inside backward between two kernel launches: record an event only, enqueue the exchange later
@@ -322,7 +339,7 @@ class FusedGradientExchange:
         self._flush_pending()
         lay = self.layout
         n = int(np.prod(lay.shapes[pi]))
-        if not pushed:                                  # computed locally: plain all-reduce of that range
+        if not pushed:                                  # computed locally: exchanged like the small tensors
             self.ranges.held.append((lay.offsets[pi], lay.offsets[pi] + n))
             return
         self.pushed += 1
@@ -343,25 +360,52 @@ class FusedGradientExchange:
         for ev, pi in pending:
             self.comm.wait_event(ev)
             shard = int(np.prod(lay.shapes[pi])) // self.world
-            self._barrier()                             # every rank's pushes have landed
             grads = self.bucket_mem.offset_table(lay.offsets[pi] * 4)
             slots_local = self.slots.local + self.slot_off[pi] * 4
-            L.check(L.lib.nk_reduce_bcast(self.comm_device.ctx, C.c_void_p(slots_local), grads, self.world, self.rank,
-                                          shard, self.reduce_ctas), self.comm_device.ctx)
-            self._barrier()                             # every owner's sums have landed
-        self._all_reduce_rest()      # biases etc. that became ready meanwhile ride behind it on the side stream
+            L.check(L.lib.nk_reduce_exchange(self.comm_device.ctx, C.c_void_p(slots_local), grads, self.flags.table,
+                                             self.world, self.rank, shard, self.state.ptr, self.reduce_ctas),
+                    self.comm_device.ctx)
 
-    def _all_reduce_rest(self) -> None:
+    def _nccl(self) -> None:
+        """Context-owned NCCL communicator on the side stream (nk_comm_init_rank); the id travels over the process group."""
+        import ctypes as C
         import torch.distributed as dist
+        from . import _lib as L
+        if self._nccl_ready:
+            return
+        box = [None]
+        if self.rank == 0:
+            buf = C.create_string_buffer(128)
+            L.check(L.lib.nk_comm_unique_id(self.comm_device.ctx, buf), self.comm_device.ctx)
+            box[0] = bytes(buf.raw)
+        dist.broadcast_object_list(box, src=0)
+        L.check(L.lib.nk_comm_init_rank(self.comm_device.ctx, self.world, self.rank, C.create_string_buffer(box[0], 128)),
+                self.comm_device.ctx)
+        self._nccl_ready = True
+
+    def _exchange_rest(self) -> None:
+        from . import _lib as L
+        import ctypes as C
         rest = self.ranges.flush()
-        if rest:
-            ev = self._events[self._ev_i % len(self._events)]
-            self._ev_i += 1
-            ev.record(self.compute)
-            self.comm.wait_event(ev)
-            with self.torch.cuda.stream(self.comm):
-                for lo, hi in rest:
-                    dist.all_reduce(self.flat[lo:hi])
+        if not rest:
+            return
+        ev = self._events[self._ev_i % len(self._events)]
+        self._ev_i += 1
+        ev.record(self.compute)
+        self.comm.wait_event(ev)
+        slot_cursor = 0
+        for lo, hi in rest:
+            n = hi - lo
+            grad = self.bucket_mem.local + lo * 4
+            if n <= self.SMALL_MAX and (slot_cursor + n) * self.world * 4 <= self.small_slots.nbytes:
+                slots = self.small_slots.offset_table(slot_cursor * self.world * 4)
+                L.check(L.lib.nk_peer_allreduce_small(self.comm_device.ctx, C.c_void_p(grad), slots,
+                                                      self.flags.offset_table(256), self.world, self.rank, n,
+                                                      C.c_void_p(self.state.ptr.value + 16)), self.comm_device.ctx)
+                slot_cursor += n
+            else:
+                self._nccl()
+                L.check(L.lib.nk_allreduce_sum(self.comm_device.ctx, C.c_void_p(grad), n, 0), self.comm_device.ctx)
 
     @property
     def launches(self) -> int:
@@ -370,5 +414,5 @@ class FusedGradientExchange:
     def wait(self) -> None:
         self._flush_pending()
         if self.ranges.held:
-            self._all_reduce_rest()
+            self._exchange_rest()
         self.compute.wait_stream(self.comm)

@@ -13,7 +13,9 @@ def test_fused_exchange_matches_all_reduce():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs two GPUs")
-    world = 2
+    world = int(os.environ.get("NK_DP_TEST_WORLD", "2"))
+    if world > n:
+        pytest.skip(f"needs {world} GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29641", os.path.join(root, "tests", "dp_worker.py")]

