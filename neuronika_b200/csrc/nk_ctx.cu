@@ -222,7 +222,18 @@ int nk_free(nk_ctx* ctx, void* dptr) {
     ctx->deferred_frees.push_back(dptr);
     return NK_OK;
   }
-  NK_CUDA(ctx, cudaFreeAsync(dptr, ctx->stream));
+  cudaError_t e = cudaFreeAsync(dptr, ctx->stream);
+  if (e == cudaErrorInvalidValue) {
+    // a block of a graph that has been destroyed in the meantime (a handle outlived nk_graph_destroy): its memory went
+    // with the arena
+    const char* c = static_cast<const char*>(dptr);
+    for (auto& r : ctx->retired_arenas)
+      if (c >= r.first && c < r.first + r.second) {
+        cudaGetLastError();
+        return NK_OK;
+      }
+  }
+  NK_CUDA(ctx, e);
   return NK_OK;
 }
 
@@ -369,7 +380,10 @@ int nk_graph_destroy(nk_ctx* ctx, nk_graph* g) {
     }
   if (g->exec) cudaGraphExecDestroy(g->exec);
   if (g->graph) cudaGraphDestroy(g->graph);
-  if (g->arena) cudaFree(g->arena);
+  if (g->arena) {
+    cudaFree(g->arena);
+    ctx->retired_arenas.emplace_back(g->arena, g->arena_bytes);
+  }
   delete g;
   return NK_OK;
 }

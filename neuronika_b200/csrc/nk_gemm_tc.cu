@@ -389,7 +389,12 @@ int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
     smem += kRsStageBytes;
   }
   kern<<<grid, kNumThreads, smem, ctx->stream>>>(ta, tb, p);
-  NK_LAUNCHED(ctx, "gemm_tcgen05");
+  ctx->launches++;
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess)
+    return nk_set_error(ctx, NK_ERR_CUDA, "launch of gemm_tcgen05 failed: %s (M=%lld N=%lld K=%lld BLOCK_N=%d grid=%d smem=%zu "
+                        "a_mn=%d b_mn=%d out=%s)", cudaGetErrorString(le), (long long)p.M, (long long)p.N, (long long)p.K,
+                        BLOCK_N, grid, smem, int(A_MN), int(B_MN), sizeof(TC) == 4 ? "f32" : "bf16");
   return NK_OK;
 }
 

@@ -201,6 +201,7 @@ static inline void grad_written(const GradientP& g) {
 struct Backward {
   GradientP gradient;  // gradient of this node's output
   bool skip = false;
+  int runs = 0;        // backward() calls so far (a second pass over the same tape must see un-aliased gradients)
   virtual ~Backward() {}
   virtual void backward() = 0;
   virtual void targets(std::vector<Gradient*>& out) = 0;  // gradients this node accumulates into
@@ -1179,6 +1180,32 @@ int nkg_backward(nkg_var* v, float seed) {
     if (!v || !v->diff()) fail(NK_ERR_INVALID_ARG, "nkg_backward: not a differentiable variable");
     if (v->fwd_buf.size() != v->fwd.size() || v->bwd_buf.size() != v->bwd.size())
       fail(NK_ERR_INVALID_ARG, "Perhaps you forgot to call .forward()?");  // vardiff.rs:126-130
+    // The aliasing peephole (dL += G with one consumer => L.grad IS G) is exact for ONE backward pass per tape.  The
+    // reference accumulates into every gradient, intermediates included, on every pass (nothing zeroes them), so on a
+    // repeated backward() the addend's gradient and the sum's gradient diverge: give the addend its own buffer, holding
+    // what the reference would hold after the passes so far (= the sum's gradient at the end of the last pass).
+    for (auto& op : v->bwd_buf) {
+      auto ab = std::dynamic_pointer_cast<AdditionBackward>(op);
+      if (!ab || !ab->left_aliased || ab->runs == 0 || !ab->left_grad || !ab->left_grad->alias) continue;
+      Gradient* g = ab->left_grad.get();
+      Gradient* src = g->root();
+      const size_t bytes = size_t(g->n()) * esize(g->dtype);
+      void* own = nullptr;
+      ck(g->ctx, nk_alloc_uninit(g->ctx, bytes, &own));
+      ck(g->ctx, nk_d2d(g->ctx, own, src->get(), bytes));
+      g->alias.reset();
+      g->ptr = own;
+      g->owned = true;
+      g->is_zero = false;
+      g->stale = false;
+      ab->left_aliased = false;
+      if (ab->right_aliased) {  // the bias gradient rode along with the convolution's dW: back to its own un-broadcast
+        for (auto& op2 : v->bwd_buf)
+          if (auto cb = std::dynamic_pointer_cast<ConvolutionBackward>(op2))
+            if (cb->bias_grad == ab->right_grad) cb->bias_grad.reset();
+        ab->right_aliased = false;
+      }
+    }
     v->grad->fill(seed);
     // last writer (reverse tape position) of every hooked gradient in this pass
     std::vector<Gradient*> tg;
@@ -1205,7 +1232,10 @@ int nkg_backward(nkg_var* v, float seed) {
     pos = 0;
     for (auto it = v->bwd_buf.rbegin(); it != v->bwd_buf.rend(); ++it, ++pos) {
       g_bwd_pos = any_hook ? pos : -2;
-      if (!(*it)->skip) (*it)->backward();
+      if (!(*it)->skip) {
+        (*it)->backward();
+        (*it)->runs++;
+      }
       if (any_hook) {  // nodes that do not report their writes individually: fire at node granularity
         tg.clear();
         (*it)->targets(tg);

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "nk_b200.h"
@@ -47,6 +48,7 @@ struct nk_ctx {
   std::multimap<size_t, void*> arena_free;      // (rounded size -> block) freed during the running capture
   std::map<void*, size_t> capturing_sizes;      // rounded size of every block handed out by the running capture
   std::vector<nk_graph*> graphs;
+  std::vector<std::pair<char*, size_t>> retired_arenas;  // ranges of destroyed graphs (late frees of their blocks are no-ops)
   std::vector<void*> deferred_frees;            // pool memory released while capturing: freed for real at capture end
   // NCCL communicator owned by the context (nk_comm.cu; libnccl is bound at run time)
   void* comm = nullptr;
