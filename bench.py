@@ -355,6 +355,8 @@ def run_own(args):
 
     import neuronika_b200 as nk
 
+    from neuronika_b200 import variable as V
+    V.set_fusion(args.fusion)
     env = Env()
     env.args, env.torch, env.dist = args, torch, dist
     world = env.world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -555,7 +557,7 @@ def run_own(args):
         "scaling": main["scaling"], "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "samples_per_s": main["samples_per_s"], "ms_per_step_stats": main["ms_per_step_stats"],
         "config": {"workload": main["workload"], "grad_dtype": args.grad_dtype, "parallelism": f"dp{world}",
-                   "exchange": main["exchange"], "cuda_graph": main["cuda_graph"],
+                   "exchange": main["exchange"], "cuda_graph": main["cuda_graph"], "fusion_level": args.fusion,
                    "step": "zero_grad -> build graph -> forward -> backward"
                            + ({"none": "", "nccl": " (+ overlapped nccl all_reduce of each layer's grad slice)",
                                "fused": " (dW GEMM epilogue reduce-scatters over NVLink peer memory; one barrier+reduce+"
@@ -828,6 +830,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--sustain-s", type=float, default=1.5)
+    ap.add_argument("--fusion", type=int, default=2, choices=[0, 1, 2],
+                    help="host-side peephole level (nkg_set_fusion): 2 = also ReLU backward in the dX GEMM epilogue")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every step eagerly (no CUDA graph)")
     ap.add_argument("--profile", action="store_true",
                     help="only the warm-up + timed steps (no e2e / roofline / cpu legs): for ncu launch lists")

@@ -114,6 +114,14 @@ int nk_gemm_bias_act(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, 
                      const void* bias /* N elements, c_dtype or f32 */, int bias_dtype,
                      int relu);
 
+/* C = beta*C + relu'(relu_operand) (.) (op(A).op(B)): the input gradient of a matmul whose left operand is the output
+ * of a ReLU, with that ReLU's backward (relu/mod.rs:71-78: dx += (x > 0) * g) applied in the GEMM epilogue instead of a
+ * separate pass over the (M, N) gradient.  relu_operand is (M, N) with C's element type and leading dimension; either
+ * the ReLU's input or its output (y = max(x, 0) > 0  <=>  x > 0). */
+int nk_gemm_relu_bwd(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A,
+                     int64_t lda, const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype,
+                     int c_dtype, const void* relu_operand);
+
 /* ---- broadcasting add (addition/mod.rs:39-50, 81-135; utils.rs:97-125, 152-192) ----
  * shapes are right-aligned, up to NK_MAX_DIMS dims. */
 #define NK_MAX_DIMS 6

@@ -63,9 +63,12 @@ int nkg_backward(nkg_var* v, float seed);
 int nkg_zero_grad(nkg_var* v);
 int nkg_no_grad(nkg_var* v);
 int nkg_with_grad(nkg_var* v);
-/* host-side peephole fusion over the tape (mm_t + bias add -> one GEMM epilogue, gradient
- * aliasing through single-consumer adds).  Invisible to results; on by default. */
-int nkg_set_fusion(int enabled);
+/* host-side peephole fusion over the tape.  level 0: off.  level 1 (default): mm_t + bias add (+ ReLU) -> one GEMM
+ * epilogue, conv + bias -> one kernel, gradient aliasing through single-consumer adds; invisible to results for ANY
+ * use of the tape (a repeated backward() un-aliases first).  level 2: additionally the ReLU backward of a layer is
+ * applied in the epilogue of the dX GEMM above it (nk_gemm_relu_bwd), which never stores the intermediate gradient --
+ * exact for one backward() per tape (what a training loop does); a second backward() on such a tape fails loudly. */
+int nkg_set_fusion(int level);
 
 /* ---- operators (names follow the reference's methods) ---- */
 int nkg_mm(nkg_var* a, nkg_var* b, nkg_var** out);      /* var.rs:1034-1061, vardiff.rs:1073-1106 */

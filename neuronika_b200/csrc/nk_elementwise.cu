@@ -902,6 +902,7 @@ int nk_sgd_step(nk_ctx* ctx, void* w, int w_dtype, void* g, int g_dtype, float* 
   NK_REQUIRE(ctx, !use_mom || buf, "nk_sgd_step: momentum requires a buffer");
   int blocks = ew_blocks(ctx, n);
   const float l2x2 = 2.f * l2, omd = 1.f - dampening;
+  if (l2x2 == 0.f && grad_scale == 1.f) write_back_grad = 0;  // g' == g: storing it back would only move bytes
 #define NK_SGD(TW, TG)                                                                                         \
   sgd_kernel<TW, TG><<<blocks, kThreads, 0, ctx->stream>>>((TW*)w, (TG*)g, buf, master, n, lr, l2x2, momentum, omd, \
                                                             use_mom, nesterov, grad_scale, write_back_grad)

@@ -38,6 +38,8 @@ struct GemmParams {
   float alpha, beta;
   int bias_bf16;
   int relu;
+  const void* mask;    // optional (M, N) tensor of C's element type and leading dimension: v = mask > 0 ? v : 0 before the
+                       // beta accumulate -- the ReLU backward of the layer below fused into the dX GEMM (relu/mod.rs:71-78)
   int num_m_blocks, num_n_blocks, num_k_blocks;
   // UMMA descriptor parameters (bytes)
   uint32_t a_lbo, a_sbo, a_kstep;
@@ -56,6 +58,25 @@ __device__ __forceinline__ int tile_m_block(const GemmParams& p, int tile) {
   // stores are spread evenly over the whole kernel and over all links instead of bunching up at the end
   const int owner = (t + p.m_rot) % p.rs_world;
   return owner * (p.num_m_blocks / p.rs_world) + t / p.rs_world;
+}
+
+// tile index -> (m block, n block).  Tiles that run concurrently are consecutive indices (persistent CTAs stride by the
+// grid), so consecutive indices walk kGroupM m-blocks before moving to the next n-block: a wave of ~128 tiles then
+// covers a near-square 16 x 8 patch of the output and re-reads far less of A and B than an m-fastest order
+// (8192-row GEMMs of config 4 moved 2.7x their algorithmic DRAM bytes, profiles/r01_launches.md).
+constexpr int kGroupM = 16;
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
+  if (p.rs_world) {
+    m_blk = tile_m_block(p, tile);
+    n_blk = tile / p.num_m_blocks;
+    return;
+  }
+  const int group_size = kGroupM * p.num_n_blocks;
+  const int group = tile / group_size, in_group = tile - group * group_size;
+  const int first_m = group * kGroupM;
+  const int gm = min(p.num_m_blocks - first_m, kGroupM);
+  m_blk = first_m + in_group % gm;
+  n_blk = in_group / gm;
 }
 
 template <int BLOCK_N>
@@ -114,8 +135,18 @@ __device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int6
                               : static_cast<const float*>(p.bias)[col0 + j];
     }
   }
+  const TC* mrow = p.mask ? static_cast<const TC*>(p.mask) + row * p.ldc + col0 : nullptr;
   if (full && vec_ok) {
     constexpr int V = 16 / sizeof(TC);
+    if (mrow) {
+#pragma unroll
+      for (int q = 0; q < 32 / V; ++q) {
+        NkVec<TC> mk;
+        mk.load(mrow + q * V);
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[q * V + i] = mk.get(i) > 0.f ? v[q * V + i] : 0.f;
+      }
+    }
     if (p.beta != 0.f) {
 #pragma unroll
       for (int q = 0; q < 32 / V; ++q) {
@@ -141,6 +172,7 @@ __device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int6
     for (int j = 0; j < 32; ++j) {
       if (j < ncols && col0 + j < p.N) {
         float x = v[j];
+        if (mrow) x = nk_to_f32<TC>(mrow[j]) > 0.f ? x : 0.f;
         if (p.beta != 0.f) x += p.beta * nk_to_f32<TC>(crow[j]);
         if (p.relu) x = x > 0.f ? x : 0.f;
         crow[j] = nk_from_f32<TC>(x);
@@ -202,7 +234,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile_m_block(p, tile), n_blk = tile / p.num_m_blocks;
+        int m_blk, n_blk;
+        tile_coords(p, tile, m_blk, n_blk);
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -267,13 +300,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ===================================================== epilogue (4 warps)
     const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
-    const bool vec_ok = ((p.ldc * int64_t(sizeof(TC))) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool vec_ok = ((p.ldc * int64_t(sizeof(TC))) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
     float* rs_stage = reinterpret_cast<float*>(smem_raw + (bar_base + 512 - ptx::smem_u32(smem_raw)));
     (void)rs_stage;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile_m_block(p, tile), n_blk = tile / p.num_m_blocks;
+      int m_blk, n_blk;
+      tile_coords(p, tile, m_blk, n_blk);
       const int64_t row = int64_t(m_blk) * BLOCK_M + q * 32 + lane;
       ptx::mbar_wait(tmem_full_bar(as), aphase);
       ptx::tc_fence_after();
@@ -428,7 +463,7 @@ bool nk_gemm_tcgen05_supported(int transA, int transB, int64_t M, int64_t N, int
 
 int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
                     int64_t lda, const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int c_dtype,
-                    const void* bias, int bias_dtype, int relu) {
+                    const void* bias, int bias_dtype, int relu, const void* mask) {
   if (!nk_gemm_tcgen05_supported(transA, transB, M, N, K, A, lda, B, ldb)) return NK_ERR_UNSUPPORTED;
   const bool a_mn = transA != 0;   // op(A) = A^T  -> A stored (K, M), M contiguous
   const bool b_mn = transB == 0;   // op(B) = B    -> B stored (K, N), N contiguous
@@ -461,6 +496,7 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   p.beta = beta;
   p.bias_bf16 = bias_dtype == NK_BF16;
   p.relu = relu;
+  p.mask = mask;
   p.num_m_blocks = int((M + BLOCK_M - 1) / BLOCK_M);
   p.num_n_blocks = 0;
   p.num_k_blocks = int((K + BLOCK_K - 1) / BLOCK_K);
@@ -539,7 +575,7 @@ int nk_gemm_bias_act(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, 
   const bool want_tc = ab_dtype == NK_BF16 && ctx->gemm_engine != NK_GEMM_SIMT && K > 0;
   if (want_tc) {
     int rc = nk_gemm_tcgen05(ctx, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, c_dtype, bias,
-                             bias_dtype, relu);
+                             bias_dtype, relu, nullptr);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
     if (ctx->gemm_engine == NK_GEMM_TCGEN05)
       return nk_set_error(ctx, NK_ERR_UNSUPPORTED,
@@ -550,6 +586,36 @@ int nk_gemm_bias_act(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, 
   }
   return nk_gemm_simt(ctx, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, ab_dtype, c_dtype, bias,
                       bias_dtype, relu);
+}
+
+int nk_gemm_relu_bwd(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                     const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype,
+                     const void* relu_operand) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, nk_dtype_ok(ab_dtype) && nk_dtype_ok(c_dtype), "nk_gemm_relu_bwd: bad dtype");
+  NK_REQUIRE(ctx, M >= 0 && N >= 0 && K > 0, "nk_gemm_relu_bwd: bad dimension");
+  if (M == 0 || N == 0) return NK_OK;
+  NK_REQUIRE(ctx, A && B && C && relu_operand, "nk_gemm_relu_bwd: NULL pointer");
+  NK_REQUIRE(ctx, lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "nk_gemm_relu_bwd: leading dimension too small");
+  if (ab_dtype == NK_BF16 && ctx->gemm_engine != NK_GEMM_SIMT) {
+    int rc = nk_gemm_tcgen05(ctx, transA, transB, M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, c_dtype, nullptr, NK_F32, 0,
+                             relu_operand);
+    if (rc != NK_ERR_UNSUPPORTED) return rc;
+  }
+  // operands the tensor-core engine cannot take: the product into a temporary, then the ordinary ReLU backward
+  void* tmp = nullptr;
+  int rc = nk_alloc_uninit(ctx, size_t(M) * size_t(N) * nk_dtype_size(c_dtype), &tmp);
+  if (rc) return rc;
+  rc = nk_gemm_simt(ctx, transA, transB, M, N, K, 1.f, A, lda, B, ldb, 0.f, tmp, N, ab_dtype, c_dtype, nullptr, NK_F32, 0);
+  if (rc == NK_OK) {
+    if (ldc == N) {
+      rc = nk_relu_bwd(ctx, C, relu_operand, tmp, size_t(M) * size_t(N), c_dtype, beta);
+    } else {
+      rc = nk_set_error(ctx, NK_ERR_UNSUPPORTED, "nk_gemm_relu_bwd: strided output needs the tensor-core engine");
+    }
+  }
+  nk_free(ctx, tmp);
+  return rc;
 }
 
 int nk_gemm(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,

@@ -30,7 +30,7 @@
 namespace nkg {
 
 static thread_local std::string g_error;
-static bool g_fusion = true;
+static int g_fusion = 1;  // 0 off, 1 exact for any use of the tape, 2 additionally assumes ONE backward() per tape
 static uint64_t g_next_op_id = 1;  // creation order == a topological order (history.rs:84-88)
 
 struct Error : std::runtime_error {
@@ -201,6 +201,7 @@ static inline void grad_written(const GradientP& g) {
 struct Backward {
   GradientP gradient;  // gradient of this node's output
   bool skip = false;
+  bool single_pass = false;  // a fusion that is exact for ONE backward pass was applied to this node
   int runs = 0;        // backward() calls so far (a second pass over the same tape must see un-aliased gradients)
   virtual ~Backward() {}
   virtual void backward() = 0;
@@ -270,9 +271,16 @@ struct MatMulBackward : Backward {
   TensorP left_data, right_data;
   GradientP left_grad, right_grad;  // either may be null (operand not differentiable)
   bool t;
+  // fusion level 2: the left operand is the output of a ReLU whose backward is the only reader of left_grad -- the
+  // masked product goes straight into the ReLU operand's gradient (nk_gemm_relu_bwd), left_grad is never materialised
+  TensorP left_mask;
+  GradientP left_dst;
   const char* name() const override { return t ? "MatrixMatrixMulTBackward" : "MatrixMatrixMulBackward"; }
   void targets(std::vector<Gradient*>& out) override {
-    if (left_grad) out.push_back(left_grad->root());
+    if (left_dst)
+      out.push_back(left_dst->root());
+    else if (left_grad)
+      out.push_back(left_grad->root());
     if (right_grad) out.push_back(right_grad->root());
   }
   void backward() override {
@@ -322,7 +330,13 @@ struct MatMulBackward : Backward {
         r->hook_fired = true;
       }
     }
-    if (left_grad) {  // (M,K)
+    if (left_dst) {  // (M,K), ReLU backward of the layer below in the epilogue: dZ += (Y > 0) * (G.W | G.B^T)
+      float beta;
+      void* d = left_dst->acc(&beta);
+      ck(ctx, nk_gemm_relu_bwd(ctx, 0, t ? 0 : 1, M, K, N, G, N, right_data->rptr(), t ? K : N, beta, d, K, gdt,
+                               left_dst->dtype, left_mask->rptr()));
+      grad_written(left_dst);
+    } else if (left_grad) {  // (M,K)
       float beta;
       void* d = left_grad->acc(&beta);
       if (t)  // dX += G.W      : (M,N).(N,K)   NN
@@ -1009,6 +1023,25 @@ void fuse(nkg_var* v) {
     add->fused_conv = it->second;
     it->second->skip = true;
   }
+  // level 2: ReLU backward into the epilogue of the matmul that produces its output gradient
+  if (g_fusion >= 2) {
+    for (auto& kv : v->bwd) {
+      auto rb = std::dynamic_pointer_cast<ReLUBackward>(kv.second);
+      if (!rb || rb->skip || !rb->gradient || !rb->operand_grad) continue;
+      Gradient* gh = rb->gradient.get();
+      if (gh->alias || gh->ptr || gh->is_leaf || gh->hook || rb->gradient.use_count() != 2) continue;
+      if (rb->operand_grad->dtype != gh->dtype || rb->operand_data->dtype != gh->dtype) continue;
+      for (auto& kv2 : v->bwd) {
+        auto mb = std::dynamic_pointer_cast<MatMulBackward>(kv2.second);
+        if (!mb || mb->left_dst || mb->left_grad.get() != gh) continue;
+        mb->left_mask = rb->operand_data;
+        mb->left_dst = rb->operand_grad;
+        mb->single_pass = true;
+        rb->skip = true;
+        break;
+      }
+    }
+  }
   // gradient aliasing: dL += G with identical shape/dtype and a single consumer => L.grad is G
   for (auto& kv : v->bwd) {
     auto ab = std::dynamic_pointer_cast<AdditionBackward>(kv.second);
@@ -1083,8 +1116,8 @@ extern "C" {
 
 const char* nkg_last_error(void) { return g_error.c_str(); }
 
-int nkg_set_fusion(int enabled) {
-  g_fusion = enabled != 0;
+int nkg_set_fusion(int level) {
+  g_fusion = level < 0 ? 0 : (level > 2 ? 2 : level);
   return NK_OK;
 }
 
@@ -1184,6 +1217,10 @@ int nkg_backward(nkg_var* v, float seed) {
     // reference accumulates into every gradient, intermediates included, on every pass (nothing zeroes them), so on a
     // repeated backward() the addend's gradient and the sum's gradient diverge: give the addend its own buffer, holding
     // what the reference would hold after the passes so far (= the sum's gradient at the end of the last pass).
+    for (auto& op : v->bwd_buf)
+      if (op->single_pass && op->runs > 0)
+        fail(NK_ERR_UNSUPPORTED, "this tape was optimised for ONE backward pass (fusion level 2: %s never stores the "
+             "gradient it would have to accumulate); build the graph again or use nkg_set_fusion(1)", op->name());
     for (auto& op : v->bwd_buf) {
       auto ab = std::dynamic_pointer_cast<AdditionBackward>(op);
       if (!ab || !ab->left_aliased || ab->runs == 0 || !ab->left_grad || !ab->left_grad->alias) continue;

@@ -140,6 +140,6 @@ int nk_gemm_simt(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int6
 // addressed by TMA, so that the caller may choose the SIMT engine
 int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha,
                     const void* A, int64_t lda, const void* B, int64_t ldb, float beta, void* C,
-                    int64_t ldc, int c_dtype, const void* bias, int bias_dtype, int relu);
+                    int64_t ldc, int c_dtype, const void* bias, int bias_dtype, int relu, const void* mask);
 bool nk_gemm_tcgen05_supported(int transA, int transB, int64_t M, int64_t N, int64_t K,
                                const void* A, int64_t lda, const void* B, int64_t ldb);

@@ -98,9 +98,11 @@ def _ck(rc: int) -> None:
         raise L.NkError(rc, lib.nkg_last_error().decode())
 
 
-def set_fusion(enabled: bool) -> None:
-    """Toggle the host-side peephole fusion (results are identical either way)."""
-    _ck(lib.nkg_set_fusion(int(bool(enabled))))
+def set_fusion(level) -> None:
+    """Host-side peephole fusion: False / 0 off, True / 1 (default) fusions that are invisible for any use of a tape,
+    2 additionally fuses a layer's ReLU backward into the dX GEMM above it (exact for one backward() per tape, which
+    is what a training loop does; a second backward() on such a tape raises)."""
+    _ck(lib.nkg_set_fusion(int(level)))
 
 
 class Reduction:

@@ -615,3 +615,57 @@ def test_capture_rejects_what_cannot_be_captured(nk, dev):
     r = big + big                                 # and the context still works
     r.forward()
     assert np.array_equal(r.data(), np.full((64, 64), 2.0, F32))
+
+
+def test_fusion_level_2_relu_backward_in_the_gemm_epilogue(nk, dev, O):
+    """level 2 applies a layer's ReLU backward in the epilogue of the dX GEMM above it: same gradients as level 1 (bit
+    for bit: the mask is applied before the one bf16 rounding in both), and a second backward() on such a tape fails"""
+    rng = np.random.default_rng(61)
+    sizes = [128, 512, 256, 10]
+    x = O.bf16_round(rng.uniform(-1, 1, (256, sizes[0])).astype(F32))
+    t = np.eye(10, dtype=F32)[rng.integers(0, 10, 256)]
+    init = []
+    for i, o in zip(sizes[:-1], sizes[1:]):
+        k = 1.0 / np.sqrt(i)
+        init += [rng.uniform(-k, k, (o, i)).astype(F32), rng.uniform(-k, k, (o,)).astype(F32)]
+    grads = {}
+    try:
+        for level in (1, 2):
+            nk.set_fusion(level)
+            params = [nk.from_ndarray(dev, v, nk.BF16).requires_grad(nk.F32) for v in init]
+            X, Tt = nk.from_ndarray(dev, x, nk.BF16).requires_grad(), nk.from_ndarray(dev, t, nk.BF16)
+            h = X
+            for li in range(3):
+                h = h.mm_t(params[2 * li]) + params[2 * li + 1]
+                h = h.relu() if li < 2 else h.softmax(1)
+            loss = h.mse_loss(Tt)
+            del h
+            loss.forward()
+            before = dev.launches
+            loss.backward(1.0)
+            launched = dev.launches - before
+            grads[level] = ([p.grad().copy() for p in params] + [X.grad().copy()], launched, loss.item())
+            if level == 2:
+                with pytest.raises(nk.NkError, match="ONE backward pass"):
+                    loss.backward(1.0)
+    finally:
+        nk.set_fusion(1)
+    # the 4096-wide layer's ReLU backward is gone; the one below the 10-wide layer stays a separate launch (its dX
+    # GEMM runs on the skinny CUDA-core kernel, whose result then goes through nk_relu_bwd)
+    assert grads[2][1] <= grads[1][1] - 1
+    assert grads[1][2] == grads[2][2]
+    for a, b in zip(grads[1][0], grads[2][0]):
+        assert np.array_equal(a, b)
+    # and against the oracle (bf16 operands, f32 accumulate)
+    wo = [O.bf16_round(v) for v in init]
+    h1 = O.bf16_round(O.relu_forward(O.linear_forward(x, wo[0], wo[1])))
+    h2 = O.bf16_round(O.relu_forward(O.linear_forward(h1, wo[2], wo[3])))
+    z3 = O.bf16_round(O.linear_forward(h2, wo[4], wo[5]))
+    y = O.bf16_round(O.softmax_forward(z3, 1))
+    dy = np.zeros_like(y)
+    O.mse_backward(y, t, np.float32(1.0), dy, "mean")
+    dz3 = np.zeros_like(z3)
+    O.softmax_backward(y, O.bf16_round(dy), dz3, 1)
+    dz3 = O.bf16_round(dz3)
+    dw3 = dz3.T @ h2
+    assert np.all(np.abs(grads[2][0][4] - dw3) <= 2e-2 * np.abs(dw3).max())
