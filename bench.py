@@ -767,11 +767,31 @@ def single_thread_baseline(workload: str, budget_s: float = 4.0):
             "sample": f"{what}; {len(times)} repetitions, median {dt:.3f} s, BLAS threads = 1"}
 
 
+class _all_cores:
+    """torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently turn the "all host cores" baseline into a
+    single-thread one: set the BLAS pool to the core count explicitly."""
+
+    def __enter__(self):
+        try:
+            from threadpoolctl import threadpool_limits
+            self._ctx = threadpool_limits(limits=os.cpu_count() or 1)
+            self._ctx.__enter__()
+        except Exception:
+            self._ctx = None
+        return self
+
+    def __exit__(self, *a):
+        if self._ctx is not None:
+            self._ctx.__exit__(*a)
+        return False
+
+
 def cpu_baseline(workload: str, budget_s: float = 12.0):
     cores = os.cpu_count() or 1
     sample = 4096 if workload != "conv" else 8
     fn, flops, what = cpu_step_fn(workload, sample)
-    times = _time_reps(fn, budget_s, 50)
+    with _all_cores():
+        times = _time_reps(fn, budget_s, 50)
     dt = float(np.median(times))
     out = {"value": round(flops / dt / 1e9, 2), "unit": "GFLOP/s", "cores": cores, "kind": "port",
            "sample": f"{what}; {len(times)} repetitions, median {dt:.3f} s (min {min(times):.3f}, max {max(times):.3f}), "
@@ -792,16 +812,17 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sample = 4096 if args.workload != "conv" else 8
     fn, flops, what = cpu_step_fn(args.workload, sample)
-    for _ in range(max(1, min(args.warmup, 2))):
-        fn()
     steps = max(1, min(args.steps, 20))
     times = []
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        s = time.perf_counter()
-        fn()
-        times.append(time.perf_counter() - s)
-    dt = (time.perf_counter() - t0) / steps
+    with _all_cores():
+        for _ in range(max(1, min(args.warmup, 2))):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            s = time.perf_counter()
+            fn()
+            times.append(time.perf_counter() - s)
+        dt = (time.perf_counter() - t0) / steps
     val = round(flops / dt / 1e9, 2)
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
            "steps": steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,

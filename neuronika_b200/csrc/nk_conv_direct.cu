@@ -4,6 +4,8 @@
 // path and what the reference's own golden cases (tiny, integer valued) run through.
 // Reference semantics: convolution/mod.rs:85-123 (fwd, beta = 0), :146-189 (dX, accumulate),
 // :191-226 (dW, accumulate), grouped variants :125-144, 228-294; arg checks utils.rs:427-496.
+#include <stdlib.h>
+
 #include "nk_internal.cuh"
 
 namespace {
@@ -144,6 +146,19 @@ inline int blocks_for(nk_ctx* ctx, int64_t total) {
 
 }  // namespace
 
+// Toeplitz-weight engine for thin inputs (nk_conv_tz.cu)
+bool nk_conv_tz_supported(int64_t n, int64_t cin, int64_t h, int64_t w, int64_t cout, int64_t kh, int64_t kw, const void* x,
+                          const void* y);
+int nk_conv_tz_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const void* bias, int relu, int64_t n, int64_t cin,
+                   int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw);
+static int conv_engine_override() {  // NK_CONV_ENGINE=shift|toeplitz: development knob, read once
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NK_CONV_ENGINE");
+    v = !e ? 0 : (e[0] == 's' ? 1 : 2);
+  }
+  return v;
+}
 // implemented in nk_conv_tc.cu; return NK_ERR_UNSUPPORTED to fall through to the direct kernels
 int nk_conv2d_fwd_tc(nk_ctx* ctx, void* y, const void* x, const void* w, const void* bias, int relu, int64_t n,
                      int64_t cin, int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw);
@@ -170,6 +185,10 @@ int nk_conv2d_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const void
   if (total == 0) return NK_OK;
   NK_REQUIRE(ctx, y && x && w, "nk_conv2d_fwd: NULL pointer");
   if (dtype == NK_BF16 && sh == 1 && sw == 1 && dh == 1 && dw == 1 && groups == 1) {
+    if (conv_engine_override() != 1 && !getenv("NK_CONV_DIRECT") && nk_conv_tz_supported(n, cin, h, wd, cout, kh, kw, x, y)) {
+      rc = nk_conv_tz_fwd(ctx, y, x, w, bias, relu, n, cin, h, wd, cout, kh, kw);
+      if (rc != NK_ERR_UNSUPPORTED) return rc;
+    }
     rc = nk_conv2d_fwd_tc(ctx, y, x, w, bias, relu, n, cin, h, wd, cout, kh, kw);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }

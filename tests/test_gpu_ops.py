@@ -451,6 +451,36 @@ def test_conv2d_random_f32(nk, dev, O, stride, dil, groups):
     assert np.allclose(gb.as_ndarray().ravel(), g.sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("shape,k", [((2, 3, 20, 24), (3, 3)), ((5, 3, 13, 16), (3, 3)), ((3, 1, 9, 40), (3, 3)),
+                                     ((2, 3, 10, 224), (3, 3)), ((1, 2, 7, 8), (3, 3)), ((2, 4, 9, 32), (2, 5)),
+                                     ((2, 4, 6, 24), (2, 1)), ((3, 3, 30, 64), (3, 9)), ((300, 3, 8, 16), (3, 3))])
+def test_conv2d_toeplitz_forward(nk, dev, O, shape, k):
+    """the thin-input kernel (expanded weights, raw image rows as the UMMA operand, aligned-span copy-out): partial
+    row blocks (Ho % 4 != 0), partial 8-pixel groups, every tap width up to 9, widths up to 224 pixels,
+    more tiles than SMs"""
+    from neuronika_b200 import ops
+    rng = np.random.default_rng(sum(shape) + k[1])
+    x = O.bf16_round(rnd(rng, shape, -1, 1))
+    w = O.bf16_round(rnd(rng, (64, shape[1]) + k, -0.3, 0.3))
+    b = O.bf16_round(rnd(rng, (64,), -0.2, 0.2))
+    dx_, dw_, db_ = dev.from_ndarray(x, nk.BF16), dev.from_ndarray(w, nk.BF16), dev.from_ndarray(b, nk.BF16)
+    ho, wo = shape[2] - k[0] + 1, shape[3] - k[1] + 1
+    # canaries around the output: the aligned-span copy-out must not write a byte outside y
+    big = dev.full((shape[0] * 64 * ho * wo + 64,), 7.0, nk.BF16)
+    y = big.slice_flat(32, (shape[0], 64, ho, wo))
+    ops.conv2d(dx_, dw_, out=y)
+    assert dev.last_conv_kernel == "tcgen05_toeplitz_fwd"
+    want = O.conv_forward(x, w, (1, 1), (1, 1)).astype(np.float64)
+    scale = float(np.sqrt((want ** 2).mean())) + 1e-9
+    got = big.as_ndarray()
+    assert np.all(got[:32] == 7.0) and np.all(got[-32:] == 7.0)
+    err = np.abs(y.as_ndarray() - want)
+    assert np.all(err <= 2e-3 * scale + 2.0 ** -8 * np.abs(want)), float(err.max())
+    yb = ops.conv2d(dx_, dw_, bias=db_, relu=True)
+    wb = np.maximum(want + b[None, :, None, None], 0)
+    assert np.all(np.abs(yb.as_ndarray() - wb) <= 2e-3 * scale + 2.0 ** -8 * np.abs(wb))
+
+
 @pytest.mark.parametrize("shape,cout,k", [((2, 3, 20, 24), 64, (3, 3)), ((1, 3, 224, 224), 64, (3, 3)),
                                           ((3, 8, 17, 40), 32, (3, 3)), ((2, 5, 9, 72), 100, (2, 4)),
                                           ((2, 32, 12, 32), 64, (3, 3)), ((1, 1, 6, 8), 1, (1, 1))])
@@ -464,7 +494,9 @@ def test_conv2d_tensor_core_forward(nk, dev, O, shape, cout, k):
     b = O.bf16_round(rnd(rng, (cout,), -0.2, 0.2))
     dx_, dw_, db_ = dev.from_ndarray(x, nk.BF16), dev.from_ndarray(w, nk.BF16), dev.from_ndarray(b, nk.BF16)
     y = ops.conv2d(dx_, dw_)
-    assert dev.last_conv_kernel == "tcgen05_implicit_gemm_fwd"
+    # thin inputs (Cin*kh <= 9, Cout = 64, W % 8 == 0, Wo even) take the Toeplitz-weight kernel, the rest the shift one
+    thin = shape[1] * k[0] <= 9 and cout == 64 and shape[3] % 8 == 0 and (shape[3] - k[1] + 1) % 2 == 0
+    assert dev.last_conv_kernel == ("tcgen05_toeplitz_fwd" if thin else "tcgen05_implicit_gemm_fwd")
     want = O.conv_forward(x, w, (1, 1), (1, 1)).astype(np.float64)
     scale = float(np.sqrt((want ** 2).mean())) + 1e-9
     err = np.abs(y.as_ndarray() - want)
