@@ -42,8 +42,8 @@ constexpr int kGroups = 32;         // 16-byte groups per image row in shared me
 constexpr int kRowPitch = kGroups * 16;
 constexpr int kMaxSteps = 9;        // (c, i) pairs: Cin * kh <= 9
 constexpr int kStepBytes = 512 * 32;  // T of one K-step: 512 rows (o, dq) x 16 du x 2 B
-constexpr int kStages = 3;
-constexpr int kSlabCh = 2;          // channels per staging slab
+constexpr int kStages = 2;
+constexpr int kSlabCh = 4;          // channels per staging slab
 constexpr int kEpiGroups = 4;       // channel quarters, each with its own pair of slabs and its own named barrier
 constexpr int kChPitch = 1808;      // bytes per staged channel: 4 rows x 444 B + 16 B of misalignment, 16-byte multiple
 constexpr int kSlabBytes = kSlabCh * kChPitch;
@@ -75,6 +75,14 @@ __device__ __forceinline__ void named_barrier(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// shared -> global bulk copy (dst and src 16-byte aligned, size a multiple of 16), tracked by bulk async-groups
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -90,7 +98,20 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16_nowait(uint32_t taddr, uint32
       : "memory");
 }
 
-template <bool kRelu>
+__device__ __forceinline__ void tmem_ld_32x32b_x32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <bool kBias, bool kRelu>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_tz_kernel(const __grid_constant__ CUtensorMap tmap_x, const TzP p) {
   extern __shared__ uint8_t smem_raw[];
@@ -144,7 +165,7 @@ conv_fwd_tz_kernel(const __grid_constant__ CUtensorMap tmap_x, const TzP p) {
     }
     for (int hf = 0; hf < 2; ++hf) {
       ptx::mbar_init(tmem_full_bar(hf), 1);
-      ptx::mbar_init(tmem_empty_bar(hf), 8);   // one arrive per epilogue warp of the half
+      ptx::mbar_init(tmem_empty_bar(hf), 16);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -165,7 +186,7 @@ conv_fwd_tz_kernel(const __grid_constant__ CUtensorMap tmap_x, const TzP p) {
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int img = tile / p.blocks_per_img, blk = tile - img * p.blocks_per_img;
-        ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+        ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);   // two tiles of slack: do not spin on the issue slots
         ptx::mbar_expect_tx(full_bar(stage), p.stage_bytes);
         // box {256 (W, zero filled beyond w), in_rows (H, zero filled beyond h), cin}
         ptx::tma_load_3d(base + x_off + stage * p.stage_bytes, &tmap_x, full_bar(stage), 0, blk * kRowsPerTile, img * p.cin);
@@ -182,11 +203,12 @@ conv_fwd_tz_kernel(const __grid_constant__ CUtensorMap tmap_x, const TzP p) {
       int stage = 0;
       uint32_t phase = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::mbar_wait_relaxed(full_bar(stage), phase);
         ptx::tc_fence_after();
         const uint32_t xs = base + x_off + stage * p.stage_bytes;
         for (int hf = 0; hf < 2; ++hf) {
-          ptx::mbar_wait(tmem_empty_bar(hf), aphase ^ 1u);
+          // the drain of the OTHER half (~4 000 cycles) hides this half's wake-up + 9 UMMAs (~1 200): relaxed wait
+          ptx::mbar_wait_relaxed(tmem_empty_bar(hf), aphase ^ 1u);
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + uint32_t(hf * 256);
           for (int s = 0; s < p.steps; ++s) {
@@ -209,99 +231,108 @@ conv_fwd_tz_kernel(const __grid_constant__ CUtensorMap tmap_x, const TzP p) {
     }
   } else {
     // ===================================================== epilogue: 4 channel quarters x 4 TMEM lane quarters
+    // All per-element address arithmetic is 32-bit and relative to one 64-bit base per tile: the first version spent 97
+    // instructions per 16 bytes of output (24.5 k warp instructions per tile against a budget of ~10 k at the HBM bound).
     const int e = warp_idx - 2;          // 0..15
-    const int cq = e >> 2;               // channel quarter: channels 16*cq .. 16*cq+15
-    const int hf = cq >> 1;              // the TMEM half (32 channels) those live in
+    const int cq = e >> 2;               // warp group: 8 channels of each TMEM half
     const int q = warp_idx & 3;          // TMEM lane quarter this warp may read
     const int m = q * 32 + lane;         // pixel group (r, a)
     const int r = m >> 5, a = m & 31;
-    const int tid_g = (e & 3) * 32 + lane;   // 0..127 inside the group
-    uint8_t* sg = base_ptr + sg_off + cq * 2 * kSlabBytes;
+    const int vi = (e & 3) * 32 + lane;  // 0..127 inside the group
+    const uint32_t sg_u32 = base + sg_off + cq * 2 * kSlabBytes;
     const float* sbias = reinterpret_cast<const float*>(base_ptr + bias_off);
     const int valid_px = p.wo - 8 * a;       // pixels of this group inside the row (<= 0: none)
     const int words = valid_px >= 8 ? 4 : (valid_px > 0 ? (valid_px + 1) >> 1 : 0);   // wo even: valid_px is even
-    const int64_t ch_elems = int64_t(p.ho) * p.wo;
+    const uint32_t ch_bytes = uint32_t(p.ho) * uint32_t(p.wo) * 2u;   // < 2^31 (host check)
     const uint32_t pix_off = uint32_t((r * p.wo + 8 * a) * 2);
-    constexpr int kSlabs = 16 / kSlabCh;     // slabs per tile and group
+    constexpr int kSlabs = 8 / kSlabCh;      // slabs per tile, half and group (8 channels)
     uint32_t aphase = 0;
-    int slab_sel = 0;
+    uint32_t slab_sel = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int img = tile / p.blocks_per_img, blk = tile - img * p.blocks_per_img;
       const int r0 = blk * kRowsPerTile;
       const int rows_valid = min(kRowsPerTile, p.ho - r0);
-      const bool writer = r < rows_valid && words > 0;
-      // first channel of the group in this tile: global element offset and address
-      const int64_t g_el0 = ((int64_t(img) * p.cout + cq * 16) * p.ho + r0) * p.wo;
-      const uintptr_t g_addr0 = reinterpret_cast<uintptr_t>(p.y) + uintptr_t(g_el0) * 2;
-      const int64_t bytes = int64_t(rows_valid) * p.wo * 2;   // contiguous bytes of one channel in this tile
-      ptx::mbar_wait(tmem_full_bar(hf), aphase);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(hf * 256 + (cq & 1) * 128);
-      uint32_t v[kSlabCh * 8];
-      tmem_ld_32x32b_x16_nowait(taddr, v);
+      const bool row_ok = r < rows_valid;
+      const bool w0 = row_ok && words > 0, w1 = row_ok && words > 1, w2 = row_ok && words > 2, w3 = row_ok && words > 3;
+      const uint32_t bytes = uint32_t(rows_valid * p.wo * 2);   // contiguous bytes of one channel in this tile
+      // ALL sixteen warps drain half 0 while the tensor core computes half 1 (and vice versa): a group never idles
+      // while "its" accumulator is recomputed
 #pragma unroll 1
-      for (int sl = 0; sl < kSlabs; ++sl) {
-        uint8_t* slab = sg + slab_sel * kSlabBytes;
-        ptx::tmem_ld_wait();
-        if (writer) {
+      for (int hf = 0; hf < 2; ++hf) {
+        const int ch0 = hf * 32 + cq * 8;      // first channel of this group in this half
+        // the one 64-bit address: channel ch0, first row of the tile
+        uint8_t* const g_base = reinterpret_cast<uint8_t*>(p.y) + (((int64_t(img) * p.cout + ch0) * p.ho + r0) * p.wo) * 2;
+        const uint32_t shift0 = uint32_t(reinterpret_cast<uintptr_t>(g_base)) & 15u;
+        ptx::mbar_wait(tmem_full_bar(hf), aphase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(hf * 256 + cq * 64);
+        uint32_t v[kSlabCh * 8];
+        tmem_ld_32x32b_x32_nowait(taddr, v);
+#pragma unroll 1
+        for (int sl = 0; sl < kSlabs; ++sl) {
+          const uint32_t slab = sg_u32 + slab_sel * kSlabBytes;
+          auto shift_of = [&](int cc) { return (shift0 + uint32_t(sl * kSlabCh + cc) * ch_bytes) & 15u; };
+          ptx::tmem_ld_wait();
 #pragma unroll
           for (int cc = 0; cc < kSlabCh; ++cc) {
-            const int ol = sl * kSlabCh + cc;               // channel inside the group
-            const float b = sbias[cq * 16 + ol];
+            const float b = kBias ? sbias[ch0 + sl * kSlabCh + cc] : 0.f;
             // same misalignment as the global address of the channel's span in this tile
-            const uint32_t shift = uint32_t((g_addr0 + uintptr_t(ol) * uintptr_t(ch_elems) * 2) & 15);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(slab + cc * kChPitch + shift + pix_off);
+            const uint32_t dst = slab + cc * kChPitch + shift_of(cc) + pix_off;
             uint32_t w4[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              float f0 = __uint_as_float(v[cc * 8 + 2 * k]) + b, f1 = __uint_as_float(v[cc * 8 + 2 * k + 1]) + b;
+              float f0 = __uint_as_float(v[cc * 8 + 2 * k]), f1 = __uint_as_float(v[cc * 8 + 2 * k + 1]);
+              if (kBias) f0 += b, f1 += b;
               if (kRelu) f0 = fmaxf(f0, 0.f), f1 = fmaxf(f1, 0.f);
               w4[k] = pack2(f0, f1);
             }
-            if (words == 4) {
-              dst[0] = w4[0], dst[1] = w4[1], dst[2] = w4[2], dst[3] = w4[3];
-            } else {
-#pragma unroll
-              for (int k = 0; k < 3; ++k)
-                if (k < words) dst[k] = w4[k];
+            // four predicated stores, no branches
+            asm volatile(
+                "{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+                "setp.ne.b32 p0, %5, 0;\n\tsetp.ne.b32 p1, %6, 0;\n\tsetp.ne.b32 p2, %7, 0;\n\tsetp.ne.b32 p3, %8, 0;\n\t"
+                "@p0 st.shared.b32 [%0], %1;\n\t@p1 st.shared.b32 [%0+4], %2;\n\t@p2 st.shared.b32 [%0+8], %3;\n\t"
+                "@p3 st.shared.b32 [%0+12], %4;\n\t}"
+                ::"r"(dst), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]), "r"(w4[3]), "r"(int(w0)), "r"(int(w1)), "r"(int(w2)), "r"(int(w3))
+                : "memory");
+          }
+          // the registers are free again: fetch the next slab's columns while this one is copied out
+          if (sl + 1 < kSlabs) tmem_ld_32x32b_x32_nowait(taddr + uint32_t((sl + 1) * kSlabCh * 8), v);
+          // ---- copy-out.  The body of each channel's span (16-byte aligned start, multiple of 16 bytes) leaves through
+          // the bulk-copy engine: ONE instruction per channel instead of 111 LDS.128 + STG.128 pairs; <= 3 head and <= 3
+          // tail words per channel go out as words.
+          ptx::fence_proxy_async();                 // this thread's slab writes -> visible to the async proxy
+          if (vi < kSlabCh) bulk_wait_read_all();   // this thread's bulk reads of the other slab are done: it may be rewritten
+          named_barrier(1 + cq, 128);               // the slab is complete
+          if (vi < kSlabCh) {                       // threads 0..3: one channel each
+            const int cc = vi;
+            const uint32_t head = (16u - shift_of(cc)) & 15u;
+            const uint32_t body = (bytes - head) & ~15u;
+            if (body) bulk_store(g_base + uint32_t(sl * kSlabCh + cc) * ch_bytes + head, slab + cc * kChPitch + shift_of(cc) + head, body);
+            bulk_commit();
+          } else if (vi >= 32 && vi < 32 + kSlabCh * 8) {   // threads 32..63: (channel, word): words 0..2 head, 4..6 tail
+            const int cc = (vi - 32) >> 3, t = (vi - 32) & 7;
+            const uint32_t sh = shift_of(cc);
+            const uint32_t head = (16u - sh) & 15u;
+            const uint32_t body = (bytes - head) & ~15u;
+            const uint32_t head_w = head >> 2, tail_w = (bytes - head - body) >> 2;
+            uint32_t off = 0xffffffffu;
+            if (uint32_t(t) < head_w) off = uint32_t(t) * 4u;
+            else if (t >= 4 && uint32_t(t - 4) < tail_w) off = head + body + uint32_t(t - 4) * 4u;
+            if (off != 0xffffffffu) {
+              uint32_t wv;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(wv) : "r"(slab + cc * kChPitch + sh + off));
+              *reinterpret_cast<uint32_t*>(g_base + uint32_t(sl * kSlabCh + cc) * ch_bytes + off) = wv;
             }
           }
+          slab_sel ^= 1u;
         }
-        // the registers are free again: fetch the next slab's columns while this one is copied out
-        if (sl + 1 < kSlabs) tmem_ld_32x32b_x16_nowait(taddr + uint32_t((sl + 1) * kSlabCh * 8), v);
-        named_barrier(1 + cq, 128);   // the slab is complete (and the other slab's copy-out of the previous round is done)
-        // ---- copy-out: per channel one contiguous span, aligned 16-byte stores + <= 3 words of head and tail
-        for (int idx = tid_g; idx < kSlabCh * 128; idx += 128) {
-          const int cc = idx >> 7, vi = idx & 127;
-          const int ol = sl * kSlabCh + cc;
-          uint8_t* gptr = reinterpret_cast<uint8_t*>(g_addr0 + uintptr_t(ol) * uintptr_t(ch_elems) * 2);
-          const uint32_t shift = uint32_t(reinterpret_cast<uintptr_t>(gptr) & 15);
-          const uint8_t* src = slab + cc * kChPitch + shift;   // byte b of the span is at src[b]
-          const int head = (16 - int(shift)) & 15;             // bytes before the first aligned vector (multiple of 4)
-          const int64_t body = (bytes - head) & ~int64_t(15);
-          const int nvec = int(body >> 4);
-          if (vi < nvec) {
-            const uint4 val = *reinterpret_cast<const uint4*>(src + head + vi * 16);   // 16-byte aligned in smem too
-            *reinterpret_cast<uint4*>(gptr + head + int64_t(vi) * 16) = val;
-          } else {
-            // lanes past the body: nvec + 0..2 write the head words, nvec + 4..6 the tail words
-            const int t = vi - nvec;
-            const int head_w = head >> 2, tail_w = int((bytes - head - body) >> 2);
-            if (t < head_w)
-              *reinterpret_cast<uint32_t*>(gptr + t * 4) = *reinterpret_cast<const uint32_t*>(src + t * 4);
-            else if (t >= 4 && t - 4 < tail_w) {
-              const int64_t off = head + body + (t - 4) * 4;
-              *reinterpret_cast<uint32_t*>(gptr + off) = *reinterpret_cast<const uint32_t*>(src + off);
-            }
-          }
-        }
-        slab_sel ^= 1;
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(hf));
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(hf));
       aphase ^= 1u;
     }
+    bulk_wait_all();   // every bulk store this thread issued has been written before the CTA retires
   }
 
   ptx::tc_fence_before();
@@ -329,6 +360,7 @@ bool nk_conv_tz_supported(int64_t n, int64_t cin, int64_t h, int64_t w, int64_t 
   if (wo % 2 != 0) return false;                               // rows of y start 4-byte aligned
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 3)) return false;
   if (int64_t(kRowsPerTile) * wo * 2 + 16 > kChPitch) return false;
+  if (ho * wo * 2 >= (int64_t(1) << 31)) return false;
   if (n * cin > (int64_t(1) << 30)) return false;
   const size_t smem = size_t(cin * kh) * kStepBytes + size_t(kStages) * size_t(cin * (kRowsPerTile + kh - 1) * kRowPitch) + 512 +
                       kEpiGroups * 2 * kSlabBytes + 256 + 256 + 128;
@@ -366,15 +398,21 @@ int nk_conv_tz_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const voi
   if (smem > 232448) return nk_set_error(ctx, NK_ERR_UNSUPPORTED, "conv tz: %zu bytes of shared memory", smem);
   static bool attr_done[64] = {};
   if (!attr_done[ctx->device & 63]) {
-    NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tz_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tz_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tz_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tz_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tz_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tz_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_done[ctx->device & 63] = true;
   }
   int grid = ctx->sm_count < p.num_tiles ? ctx->sm_count : p.num_tiles;
-  if (relu)
-    conv_fwd_tz_kernel<true><<<grid, kThreads, smem, ctx->stream>>>(tm, p);
+  if (bias && relu)
+    conv_fwd_tz_kernel<true, true><<<grid, kThreads, smem, ctx->stream>>>(tm, p);
+  else if (bias)
+    conv_fwd_tz_kernel<true, false><<<grid, kThreads, smem, ctx->stream>>>(tm, p);
+  else if (relu)
+    conv_fwd_tz_kernel<false, true><<<grid, kThreads, smem, ctx->stream>>>(tm, p);
   else
-    conv_fwd_tz_kernel<false><<<grid, kThreads, smem, ctx->stream>>>(tm, p);
+    conv_fwd_tz_kernel<false, false><<<grid, kThreads, smem, ctx->stream>>>(tm, p);
   NK_LAUNCHED(ctx, "conv_fwd_tz");
   ctx->last_conv_kernel = "tcgen05_toeplitz_fwd";
   return NK_OK;
