@@ -485,7 +485,10 @@ def run_own(args):
             ach = spec["bytes_per_rank_step"] / per_rank / 1e9
             out["step_roofline"] = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": round(ach / peaks["hbm_gbs"], 4),
-                                    "algorithmic_bytes_per_step": spec["bytes_per_rank_step"]}
+                                    "algorithmic_bytes_per_step": spec["bytes_per_rank_step"],
+                                    "note": "algorithmic bytes as SURVEY.md 8-d defines them (x, y, G, x, dx each once, bf16); "
+                                            "the resident step seeds the root with backward(seed), whose uniform gradient the "
+                                            "backward kernel synthesises instead of reading, so its DRAM traffic is lower"}
         else:
             ach = spec["flops_per_rank_step"] / per_rank / 1e12
             out["step_roofline"] = {"bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops_sustained"],

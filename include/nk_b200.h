@@ -245,6 +245,15 @@ int nk_conv2d_bwd(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int dw_dtype,
                   float beta_dw, const void* g, const void* x, const void* w, int64_t n,
                   int64_t cin, int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw,
                   int64_t sh, int64_t sw, int64_t dh, int64_t dw, int64_t groups, int dtype);
+/* The same when the output gradient is ONE value everywhere -- VarDiff::backward(seed) on the convolution's own
+ * output fills the root gradient with the seed (vardiff.rs:125-141): the kernel synthesises its G tiles from g_value
+ * (rounded to the gradient's element type first, as the fill would) instead of reading 2|G| bytes that a fill kernel
+ * would have had to write first.  Same arithmetic, same results as fill + nk_conv2d_bwd.  Returns NK_ERR_UNSUPPORTED
+ * (nothing done) for shapes outside the tensor-core engine: the caller then materialises the gradient. */
+int nk_conv2d_bwd_uniform(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int dw_dtype, void* dbias,
+                          float beta_dw, float g_value, const void* x, const void* w, int64_t n, int64_t cin,
+                          int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw, int64_t sh, int64_t sw,
+                          int64_t dh, int64_t dw, int64_t groups, int dtype);
 /* 1-D / 3-D convolution, x (N, Cin, s[0..nsp)), w (Cout, Cin/groups, k[0..nsp)), nsp = 1..3 sample dims
  * (the reference's convolution is generic over them: convolution/mod.rs:85-226, goldens
  * convolution/test.rs:144-239, 306-444 and the strided / dilated / grouped siblings).  CUDA-core gather

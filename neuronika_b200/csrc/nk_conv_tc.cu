@@ -1209,6 +1209,8 @@ struct ConvBP {
   __nv_bfloat16* dx;
   float beta_dx;
   float* scratch;
+  int use_const;        // the output gradient is one value everywhere (backward(seed) on the convolution's own output):
+  uint32_t const_bits;  // the loaders synthesise the G tiles (value packed twice as bf16) instead of reading 2|G| bytes
 };
 
 template <int CIN>
@@ -1474,6 +1476,23 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
         const uint32_t sb = base + st_off + stage * stage_bytes;
         const __nv_bfloat16* grow = p.g + (long long)n * p.cout * plane + (long long)pr * p.wo;
+        if (p.use_const) {
+          // uniform output gradient: the tile is written, not fetched (same swizzled positions, zero beyond Wo)
+#pragma unroll
+          for (int c = 0; c < kChunksPerTile; ++c) {
+            const uint32_t val = (p.wo - c * kChunk - piece * 2) > 0 ? p.const_bits : 0u;
+            uint32_t dst = sb + c * chunk_bytes + o0 * 128 + sw;
+#pragma unroll 8
+            for (int o = o0; o < p.cout; o += 8, dst += 1024)
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(val) : "memory");
+          }
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ready_bar(stage)) : "memory");
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          continue;
+        }
         if (base8 && (((long long)pr * p.wo) & 3) == 0) {
 #pragma unroll
           for (int c = 0; c < kChunksPerTile; ++c) {
@@ -1609,7 +1628,7 @@ int launch_bwd_fused(nk_ctx* ctx, const CUtensorMap& tm, const CUtensorMap& tmh,
 
 int nk_conv2d_bwd_fused_tc(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int dw_dtype, void* dbias, float beta_dw,
                            const void* g, const void* x, const void* w, int64_t n, int64_t cin, int64_t h, int64_t wd,
-                           int64_t cout, int64_t kh, int64_t kw) {
+                           int64_t cout, int64_t kh, int64_t kw, const float* g_const) {
   if (getenv("NK_CONV_DIRECT") || getenv("NK_CONV_UNFUSED_BWD")) return NK_ERR_UNSUPPORTED;
   if (!ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
   if (kh != 3 || kw != 3 || cin < 1 || cin > 3) return NK_ERR_UNSUPPORTED;
@@ -1626,6 +1645,14 @@ int nk_conv2d_bwd_fused_tc(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int 
   p.ksteps = 3 * p.ng;
   p.ncols = p.ksteps * 16;
   p.fuse_dbias = (dbias != nullptr && p.R < 16) ? 1 : 0;
+  p.use_const = g_const != nullptr;
+  p.const_bits = 0;
+  if (g_const) {
+    if (dbias && !p.fuse_dbias) return NK_ERR_UNSUPPORTED;   // the separate bias-gradient pass reads G from memory
+    const __nv_bfloat16 hv = __float2bfloat16_rn(*g_const);
+    const uint16_t hb = *reinterpret_cast<const uint16_t*>(&hv);
+    p.const_bits = uint32_t(hb) | (uint32_t(hb) << 16);
+  }
   // ONE dW accumulator: consecutive UMMAs into the same TMEM columns issue every 77 cycles, alternating accumulators
   // costs 219 cycles per instruction (tools/umma_probe.cu, profiles/r01_umma_issue_probe.txt)
   p.nacc = 1;

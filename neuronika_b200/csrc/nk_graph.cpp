@@ -109,6 +109,11 @@ struct Gradient {
   void* rs_user = nullptr;
   int last_writer = -1;             // index (in reverse tape order) of the last node writing it in this pass
   bool hook_fired = false;
+  // fill(v) is deferred: the gradient is "v everywhere" until somebody needs the bytes (get / acc materialise it).
+  // A consumer that can synthesise a uniform gradient on the fly (ConvolutionBackward -> nk_conv2d_bwd_uniform) never
+  // makes the 2|G| bytes exist: backward(seed) on a convolution's own output costs no fill and no read of G.
+  bool is_const = false;
+  float const_val = 0.f;
   bool is_leaf = false;             // created by requires_grad(): owned by the user, never aliased away by the peephole
   Gradient(nk_ctx* c, Shape s, int dt) : ctx(c), shape(std::move(s)), dtype(dt) {}
   ~Gradient() {
@@ -130,12 +135,17 @@ struct Gradient {
       ck(r->ctx, nk_memset0(r->ctx, r->ptr, size_t(r->n()) * esize(r->dtype)));
       r->stale = false;
     }
+    if (r->is_const) {  // a reader wants the bytes of a deferred fill
+      r->is_const = false;
+      ck(r->ctx, nk_fill(r->ctx, r->ptr, r->dtype, size_t(r->n()), r->const_val));
+    }
     return r->ptr;
   }
   // pointer + beta for an accumulating write that covers the whole buffer: beta = 0 when the content is
   // known to be zero (then stale memory is simply overwritten), and the buffer counts as touched afterwards
   void* acc(float* beta) {
     Gradient* r = root();
+    if (r->is_const) get();  // accumulating on top of a deferred fill: make it real first
     if (r->enabled && !r->ptr) {  // first touch is a full overwrite (beta = 0): no need to clear the new buffer
       ck(r->ctx, nk_alloc_uninit(r->ctx, size_t(r->n()) * esize(r->dtype), &r->ptr));
       r->is_zero = true;
@@ -149,6 +159,7 @@ struct Gradient {
   }
   void zero() {
     Gradient* r = root();
+    r->is_const = false;
     if (r->ptr && !r->is_zero) {
       if (r->owned)
         r->stale = true;  // owned memory: clear lazily (first full overwrite or first read)
@@ -157,14 +168,26 @@ struct Gradient {
     }
     r->is_zero = true;
   }
-  void fill(float v) {
+  void fill(float v) {  // deferred: see is_const
     Gradient* r = root();
-    float unused;
-    ck(r->ctx, nk_fill(r->ctx, acc(&unused), r->dtype, size_t(r->n()), v));
+    if (!r->enabled)
+      fail(NK_ERR_INVALID_ARG,
+           "Trying to get a de-allocated gradient. Switch on the gradients first by using `.with_grad()`");
+    if (!r->owned) {  // caller-visible memory: write it now
+      float unused;
+      r->is_const = false;
+      ck(r->ctx, nk_fill(r->ctx, acc(&unused), r->dtype, size_t(r->n()), v));
+      r->is_zero = false;
+      return;
+    }
+    r->is_const = true;
+    r->const_val = v;
     r->is_zero = false;
+    r->stale = false;
   }
   void no_grad() {  // gradient.rs:68-71
     Gradient* r = root();
+    r->is_const = false;
     if (r->owned && r->ptr) nk_free(r->ctx, r->ptr);
     if (r->owned) r->ptr = nullptr;
     r->enabled = false;
@@ -599,13 +622,23 @@ struct ConvolutionBackward : Backward {  // convolution/mod.rs:357-510: input fi
     // dX is produced in the element type of the output gradient; an input gradient of another type goes through
     // acc_typed (and then the two halves run as separate kernels)
     const bool dx_same = !input_grad || input_grad->dtype == gradient->dtype;
+    Gradient* gr = gradient->root();
     if (input_grad && kernel_grad && dx_same) {  // both halves: one pass over the output gradient where the kernels allow it
       float bx, bw;
       void* dxp = input_grad->acc(&bx);
       void* dwp = kernel_grad->acc(&bw);
-      ck(ctx, nk_conv2d_bwd(ctx, dxp, bx, dwp, kernel_grad->dtype, dbias, bw, gradient->get(), input->rptr(),
-                            kernel->rptr(), a.n, a.cin, a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups,
-                            gradient->dtype));
+      int rc = NK_ERR_UNSUPPORTED;
+      if (gr->is_const && (!bias_grad || dbias))
+        // the output gradient is a deferred fill (backward(seed) on this convolution's own output): the kernel
+        // synthesises it instead of reading 2|G| bytes that a fill would have had to write first
+        rc = nk_conv2d_bwd_uniform(ctx, dxp, bx, dwp, kernel_grad->dtype, dbias, bw, gr->const_val, input->rptr(),
+                                   kernel->rptr(), a.n, a.cin, a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw, a.dh, a.dw,
+                                   a.groups, gradient->dtype);
+      if (rc == NK_ERR_UNSUPPORTED)
+        rc = nk_conv2d_bwd(ctx, dxp, bx, dwp, kernel_grad->dtype, dbias, bw, gradient->get(), input->rptr(),
+                           kernel->rptr(), a.n, a.cin, a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups,
+                           gradient->dtype);
+      ck(ctx, rc);
       grad_written(kernel_grad);
       grad_written(input_grad);
     } else {
