@@ -11,6 +11,8 @@ Workloads (BASELINE.json configs):
   mlp     (config 4)           MLP 1024-4096-4096-10 + ReLU/Softmax, MSE, SGD step; global batch 8192 sharded
                                over the ranks (STRONG scaling), same exchange
   conv    (config 3)           nn::Conv2d 3->64 k3 s1, 224x224, batch 256 per GPU, fwd + bwd (dX, dW, db)
+  convnet (config 5)           small ConvNet (Conv2d 3->32, Conv2d 32->64, Linear) on 32x32x3, global batch 4096 sharded
+                               over the ranks, SGD step; every convolution kernel is a tcgen05 one
 
 A step of the own arm = zero_grad -> build the define-by-run graph -> forward -> backward (-> exchange -> SGD where the
 workload has them) through the package's public API (Var/VarDiff/nn/optim over the C++ graph and the C ABI).  The step
@@ -76,6 +78,17 @@ def workload_spec(name: str, world: int):
                 "shape": (n, cin, h, w), "cout": cout, "k": k, "params": cout * cin * k * k + cout,
                 "bytes_per_rank_step": 2.0 * (2 * n * cout * ho * wo + 3 * n * cin * h * w), "bound": "hbm",
                 "arena": 12 << 30}
+    if name == "convnet":
+        gb = 4096
+        assert gb % world == 0
+        b = gb // world
+        f1 = 2.0 * b * 32 * 1024 * 27
+        f2 = 2.0 * b * 64 * 1024 * 288
+        f3 = 2.0 * b * 65536 * 10
+        # fwd + dW for every layer, dX for conv2 and the Linear (the network input is not differentiable)
+        return {"name": "small ConvNet (Conv2d 3->32 p1, Conv2d 32->64 p1, Linear 65536->10) on 32x32x3, global batch 4096, SGD step",
+                "scaling": "strong", "flops_per_rank_step": 2 * f1 + 3 * f2 + 3 * f3, "samples_per_rank_step": b, "batch": b,
+                "params": 32 * 27 + 32 + 64 * 288 + 64 + 655360 + 10, "bound": "tensor", "arena": 24 << 30}
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -261,6 +274,38 @@ class Workload:
                 for li in range(3):
                     h = h.mm_t(params[2 * li]) + params[2 * li + 1]
                     h = h.relu() if li < 2 else h.softmax(1)
+                loss = h.mse_loss(inp["t"])
+                loss.forward()
+                loss.backward(1.0)
+                live["root"] = loss
+            step_e2e = step_resident
+        elif name == "convnet":
+            bsz = spec["batch"]
+            shapes = [(32, 3, 3, 3), (32, 1, 1), (64, 32, 3, 3), (64, 1, 1), (10, 65536), (10,)]
+            self.bucket, gviews = make_bucket(shapes)
+            self.params = []
+            for sh, gv in zip(shapes, gviews):
+                fan = int(np.prod(sh[1:])) if len(sh) > 1 and sh[1:] != (1, 1) else {32: 27, 64: 288, 10: 65536}[sh[0]]
+                kk = 1.0 / np.sqrt(fan)
+                self.params.append(param(rng.uniform(-kk, kk, sh).astype(np.float32), gv))
+            params = self.params
+            x_host = drng.uniform(0, 1, (bsz, 3, 32, 32)).astype(np.float32)
+            t_host = np.eye(10, dtype=np.float32)[drng.integers(0, 10, bsz)]
+            px, pt = pinned_bf16(x_host), pinned_bf16(t_host)
+
+            def make_inputs():
+                x = V.from_ndarray(dev, x_host, BF)
+                t = V.from_ndarray(dev, t_host, BF)
+                return {"x": x, "t": t, "copies": [(px, x), (pt, t)]}
+            self.opt = nk.optim.StochasticGD.new(0.01, nk.optim.L2(0.0), grad_scale=1.0 / world)
+            for p in params:
+                self.opt.register(p)
+
+            def step_resident(inp):
+                self.opt.zero_grad()
+                h = (params[0].convolution(inp["x"].pad((1, 1)), (1, 1), (1, 1), 1) + params[1]).relu()
+                h = (params[2].convolution(h.pad((1, 1)), (1, 1), (1, 1), 1) + params[3]).relu()
+                h = (h.flatten().mm_t(params[4]) + params[5]).softmax(1)
                 loss = h.mse_loss(inp["t"])
                 loss.forward()
                 loss.backward(1.0)
@@ -846,8 +891,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default="linear", choices=["linear", "mlp", "conv"])
-    ap.add_argument("--others", default="conv,mlp", help="other BASELINE configs measured in the same process ('none')")
+    ap.add_argument("--workload", default="linear", choices=["linear", "mlp", "conv", "convnet"])
+    ap.add_argument("--others", default="conv,mlp,convnet", help="other BASELINE configs measured in the same process ('none')")
     ap.add_argument("--other-steps", type=int, default=50)
     ap.add_argument("--grad-dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--master-weights", action="store_true")

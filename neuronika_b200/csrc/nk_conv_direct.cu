@@ -151,6 +151,14 @@ bool nk_conv_tz_supported(int64_t n, int64_t cin, int64_t h, int64_t w, int64_t 
                           const void* y);
 int nk_conv_tz_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const void* bias, int relu, int64_t n, int64_t cin,
                    int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw);
+// im2col + batched tcgen05 GEMM for every other bf16, groups = 1 shape (nk_conv_gemm.cu)
+int nk_conv_gemm_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const void* bias, int relu, int64_t n, int64_t cin,
+                     int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t dh, int64_t dw);
+int nk_conv_gemm_bwd_input(nk_ctx* ctx, void* dx, const void* g, const void* w, int64_t n, int64_t cin, int64_t h, int64_t wd,
+                           int64_t cout, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t dh, int64_t dw, float beta);
+int nk_conv_gemm_bwd_kernel(nk_ctx* ctx, void* dwt, int dw_dtype, const void* g, const void* x, int64_t n, int64_t cin, int64_t h,
+                            int64_t wd, int64_t cout, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t dh, int64_t dw,
+                            float beta);
 static int conv_engine_override() {  // NK_CONV_ENGINE=shift|toeplitz: development knob, read once
   static int v = -1;
   if (v < 0) {
@@ -192,6 +200,10 @@ int nk_conv2d_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const void
     rc = nk_conv2d_fwd_tc(ctx, y, x, w, bias, relu, n, cin, h, wd, cout, kh, kw);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }
+  if (dtype == NK_BF16 && groups == 1 && !getenv("NK_CONV_DIRECT")) {
+    rc = nk_conv_gemm_fwd(ctx, y, x, w, bias, relu, n, cin, h, wd, cout, kh, kw, sh, sw, dh, dw);
+    if (rc != NK_ERR_UNSUPPORTED) return rc;
+  }
   ctx->last_conv_kernel = "direct_fwd";
   int blocks = blocks_for(ctx, total);
   if (dtype == NK_BF16)
@@ -217,6 +229,10 @@ int nk_conv2d_bwd_input(nk_ctx* ctx, void* dx, const void* g, const void* w, int
     rc = nk_conv2d_bwd_input_tc(ctx, dx, g, w, n, cin, h, wd, cout, kh, kw, beta);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }
+  if (dtype == NK_BF16 && groups == 1 && !getenv("NK_CONV_DIRECT")) {
+    rc = nk_conv_gemm_bwd_input(ctx, dx, g, w, n, cin, h, wd, cout, kh, kw, sh, sw, dh, dw, beta);
+    if (rc != NK_ERR_UNSUPPORTED) return rc;
+  }
   ctx->last_conv_kernel = "direct_bwd_input";
   int blocks = blocks_for(ctx, total);
   if (dtype == NK_BF16)
@@ -240,6 +256,15 @@ int nk_conv2d_bwd_kernel(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, cons
   if (d.n * d.ho * d.wo == 0) return NK_OK;
   if (dtype == NK_BF16 && sh == 1 && sw == 1 && dh == 1 && dw == 1 && groups == 1) {
     rc = nk_conv2d_bwd_kernel_tc(ctx, dwt, dw_dtype, dbias, g, x, n, cin, h, wd, cout, kh, kw, beta);
+    if (rc != NK_ERR_UNSUPPORTED) return rc;
+  }
+  if (dtype == NK_BF16 && groups == 1 && !getenv("NK_CONV_DIRECT")) {
+    rc = nk_conv_gemm_bwd_kernel(ctx, dwt, dw_dtype, g, x, n, cin, h, wd, cout, kh, kw, sh, sw, dh, dw, beta);
+    if (rc == NK_OK && dbias) {
+      int64_t dshape[3] = {d.cout, 1, 1};
+      int64_t gshape[4] = {d.n, d.cout, d.ho, d.wo};
+      rc = nk_unbroadcast_acc(ctx, dbias, dw_dtype, 3, dshape, g, dtype, 4, gshape, beta);
+    }
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }
   ctx->last_conv_kernel = "direct_bwd_kernel";

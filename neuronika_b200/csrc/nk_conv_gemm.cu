@@ -1,0 +1,224 @@
+// General 2-D convolution on the tensor cores: im2col + batched tcgen05 GEMM (bf16, groups = 1, any stride / dilation /
+// channel count).  This is the reference's own formulation -- convolution/mod.rs:85-123 (out[n] = Wflat . cols[n]^T),
+// :146-189 (dX = col2im(G[n]^T . Wflat)), :191-226 (dW += G[n] . cols[n]) -- with the GEMMs on tcgen05 instead of one
+// sgemm per sample: ONE batched launch (3-D TMA maps over (k, row, sample)) per product, and the kernel gradient as a
+// split reduction over the samples inside the GEMM's k loop.  It takes every bf16 shape the two specialised engines
+// (nk_conv_tz.cu: thin inputs; nk_conv_tc.cu: 3x3 with Cin <= 3 backward) do not, e.g. config 5's 32 -> 64 layer;
+// only shapes TMA cannot address (Ho*Wo not a multiple of 8) fall through to the CUDA-core kernels.
+//   cols[n][l][k]  k = (c, i, j) as in the reference (utils.rs:332-353), padded with zeros to Kp = ceil8(K) so that rows
+//   are 16-byte multiples (TMA); the buffer lives in HBM for the duration of the call (sample chunks of <= 4 GB).
+// Compute bound for Cin >= 16 (K >= 144); the column buffer adds 2 x |cols| of HBM traffic.
+#include "nk_internal.cuh"
+
+int nk_gemm_tcgen05_batched(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
+                            int64_t lda, int64_t strideA, const void* B, int64_t ldb, int64_t strideB, void* C, int64_t ldc,
+                            int64_t strideC, int64_t batch, int c_dtype, const void* row_bias, int bias_dtype, int relu,
+                            int reduce);
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int64_t kChunkBytes = int64_t(4) << 30;
+
+struct CgDims {
+  int64_t n, cin, h, w, cout, kh, kw, sh, sw, dh, dw, ho, wo, K, Kp, L;
+};
+
+// cols[n][l][k8 .. k8+7]: one thread per 16-byte vector
+__global__ void __launch_bounds__(kThreads) im2col_kernel(__nv_bfloat16* __restrict__ cols, const __nv_bfloat16* __restrict__ x,
+                                                          CgDims d, int64_t n0, int64_t nn) {
+  const int64_t kv = d.Kp / 8;
+  const int64_t total = nn * d.L * kv;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int64_t v = idx % kv, l = (idx / kv) % d.L, ns = idx / (kv * d.L);
+    const int64_t p = l / d.wo, q = l - p * d.wo;
+    const __nv_bfloat16* xs = x + (n0 + ns) * d.cin * d.h * d.w;
+    __align__(16) __nv_bfloat16 out[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int64_t k = v * 8 + e;
+      if (k < d.K) {
+        const int64_t j = k % d.kw, i = (k / d.kw) % d.kh, c = k / (d.kw * d.kh);
+        out[e] = xs[(c * d.h + p * d.sh + i * d.dh) * d.w + q * d.sw + j * d.dw];
+      } else {
+        out[e] = __float2bfloat16_rn(0.f);
+      }
+    }
+    *reinterpret_cast<uint4*>(cols + idx * 8) = *reinterpret_cast<const uint4*>(out);
+  }
+}
+
+// dx[n,c,u,v] = beta*dx + sum_{i,j : u = p*sh + i*dh, v = q*sw + j*dw} dcols[n][p*wo+q][(c,i,j)]
+__global__ void __launch_bounds__(kThreads) col2im_kernel(__nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ dcols,
+                                                          CgDims d, int64_t n0, int64_t nn, float beta) {
+  const int64_t total = nn * d.cin * d.h * d.w;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int64_t v = idx % d.w, u = (idx / d.w) % d.h, c = (idx / (d.w * d.h)) % d.cin, ns = idx / (d.w * d.h * d.cin);
+    const __nv_bfloat16* dc = dcols + ns * d.L * d.Kp;
+    float acc = 0.f;
+    for (int64_t i = 0; i < d.kh; ++i) {
+      const int64_t pu = u - i * d.dh;
+      if (pu < 0 || pu % d.sh != 0) continue;
+      const int64_t p = pu / d.sh;
+      if (p >= d.ho) continue;
+      for (int64_t j = 0; j < d.kw; ++j) {
+        const int64_t qv = v - j * d.dw;
+        if (qv < 0 || qv % d.sw != 0) continue;
+        const int64_t q = qv / d.sw;
+        if (q >= d.wo) continue;
+        acc += __bfloat162float(dc[(p * d.wo + q) * d.Kp + (c * d.kh + i) * d.kw + j]);
+      }
+    }
+    __nv_bfloat16* o = dx + (n0 + ns) * d.cin * d.h * d.w + (idx - ns * d.cin * d.h * d.w);
+    if (beta != 0.f) acc += beta * __bfloat162float(*o);
+    *o = __float2bfloat16_rn(acc);
+  }
+}
+
+// (Cout, Kp) bf16 copy of the (Cout, K) kernel, zero padded (the GEMM operand rows must be 16-byte multiples)
+__global__ void __launch_bounds__(kThreads) pad_kernel_rows(__nv_bfloat16* __restrict__ wp, const __nv_bfloat16* __restrict__ w,
+                                                            int64_t cout, int64_t K, int64_t Kp) {
+  const int64_t total = cout * Kp;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t k = idx % Kp, o = idx / Kp;
+    wp[idx] = k < K ? w[o * K + k] : __float2bfloat16_rn(0.f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) finalize_dw_padded(T* __restrict__ dw, const float* __restrict__ scratch, int64_t cout,
+                                                               int64_t K, int64_t Kp, float beta) {
+  const int64_t total = cout * K;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int64_t k = idx % K, o = idx / K;
+  float v = scratch[o * Kp + k];
+  if (beta != 0.f) v += beta * nk_to_f32<T>(dw[idx]);
+  dw[idx] = nk_from_f32<T>(v);
+}
+
+inline int cg_blocks(nk_ctx* ctx, int64_t items) {
+  int64_t b = (items + kThreads - 1) / kThreads;
+  const int64_t cap = int64_t(ctx->sm_count) * 16;
+  if (b > cap) b = cap;
+  return int(b < 1 ? 1 : b);
+}
+
+bool make_dims(CgDims& d, int64_t n, int64_t cin, int64_t h, int64_t w, int64_t cout, int64_t kh, int64_t kw, int64_t sh,
+               int64_t sw, int64_t dh, int64_t dw) {
+  d = CgDims{n, cin, h, w, cout, kh, kw, sh, sw, dh, dw, 0, 0, 0, 0, 0};
+  d.ho = (h - dh * (kh - 1) - 1) / sh + 1;
+  d.wo = (w - dw * (kw - 1) - 1) / sw + 1;
+  d.K = cin * kh * kw;
+  d.Kp = (d.K + 7) & ~int64_t(7);
+  d.L = d.ho * d.wo;
+  // TMA: every leading dimension / batch stride a multiple of 8 elements; a useful amount of work per GEMM tile
+  return n > 0 && d.L > 0 && d.L % 8 == 0 && d.Kp >= 16 && d.L * d.Kp < (int64_t(1) << 31);
+}
+
+struct Scratch {   // stream-ordered temporaries released on scope exit
+  nk_ctx* ctx;
+  void* p[3] = {nullptr, nullptr, nullptr};
+  explicit Scratch(nk_ctx* c) : ctx(c) {}
+  ~Scratch() {
+    for (void* q : p)
+      if (q) nk_free(ctx, q);
+  }
+};
+
+int64_t chunk_samples(const CgDims& d) {
+  int64_t per = d.L * d.Kp * 2;
+  int64_t c = kChunkBytes / per;
+  if (c < 1) c = 1;
+  return c < d.n ? c : d.n;
+}
+
+}  // namespace
+
+// all three return NK_ERR_UNSUPPORTED (last_error untouched) when the shape is outside this engine
+
+int nk_conv_gemm_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const void* bias, int relu, int64_t n, int64_t cin,
+                     int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t dh, int64_t dw) {
+  CgDims d;
+  if (!make_dims(d, n, cin, h, wd, cout, kh, kw, sh, sw, dh, dw) || !ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(y) & 15) || cout < 8) return NK_ERR_UNSUPPORTED;
+  Scratch s(ctx);
+  int rc = nk_alloc_uninit(ctx, size_t(cout * d.Kp * 2), &s.p[0]);
+  if (rc) return rc;
+  pad_kernel_rows<<<cg_blocks(ctx, cout * d.Kp), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)s.p[0], (const __nv_bfloat16*)w, cout, d.K, d.Kp);
+  NK_LAUNCHED(ctx, "conv_pad_kernel");
+  const int64_t cs = chunk_samples(d);
+  rc = nk_alloc_uninit(ctx, size_t(cs * d.L * d.Kp * 2), &s.p[1]);
+  if (rc) return rc;
+  for (int64_t n0 = 0; n0 < n; n0 += cs) {
+    const int64_t nn = n - n0 < cs ? n - n0 : cs;
+    im2col_kernel<<<cg_blocks(ctx, nn * d.L * (d.Kp / 8)), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)s.p[1], (const __nv_bfloat16*)x, d, n0, nn);
+    NK_LAUNCHED(ctx, "im2col");
+    // y[n] (Cout x L) = Wp (Cout x Kp) . cols[n]^T : NT, A shared by every sample
+    rc = nk_gemm_tcgen05_batched(ctx, 0, 1, cout, d.L, d.Kp, 1.f, s.p[0], d.Kp, 0, s.p[1], d.Kp, d.L * d.Kp,
+                                 static_cast<__nv_bfloat16*>(y) + n0 * cout * d.L, d.L, cout * d.L, nn, NK_BF16, bias, NK_BF16,
+                                 relu, 0);
+    if (rc) return rc;
+  }
+  ctx->last_conv_kernel = "tcgen05_im2col_gemm_fwd";
+  return NK_OK;
+}
+
+int nk_conv_gemm_bwd_input(nk_ctx* ctx, void* dx, const void* g, const void* w, int64_t n, int64_t cin, int64_t h, int64_t wd,
+                           int64_t cout, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t dh, int64_t dw, float beta) {
+  CgDims d;
+  if (!make_dims(d, n, cin, h, wd, cout, kh, kw, sh, sw, dh, dw) || !ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) || cout % 8 != 0) return NK_ERR_UNSUPPORTED;
+  Scratch s(ctx);
+  int rc = nk_alloc_uninit(ctx, size_t(cout * d.Kp * 2), &s.p[0]);
+  if (rc) return rc;
+  pad_kernel_rows<<<cg_blocks(ctx, cout * d.Kp), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)s.p[0], (const __nv_bfloat16*)w, cout, d.K, d.Kp);
+  NK_LAUNCHED(ctx, "conv_pad_kernel");
+  const int64_t cs = chunk_samples(d);
+  rc = nk_alloc_uninit(ctx, size_t(cs * d.L * d.Kp * 2), &s.p[1]);
+  if (rc) return rc;
+  for (int64_t n0 = 0; n0 < n; n0 += cs) {
+    const int64_t nn = n - n0 < cs ? n - n0 : cs;
+    // dcols[n] (L x Kp) = G[n]^T (L x Cout) . Wp (Cout x Kp) : TN (A = G[n] stored (Cout, L)), B shared
+    rc = nk_gemm_tcgen05_batched(ctx, 1, 0, d.L, d.Kp, cout, 1.f, static_cast<const __nv_bfloat16*>(g) + n0 * cout * d.L, d.L,
+                                 cout * d.L, s.p[0], d.Kp, 0, s.p[1], d.Kp, d.L * d.Kp, nn, NK_BF16, nullptr, NK_BF16, 0, 0);
+    if (rc) return rc;
+    col2im_kernel<<<cg_blocks(ctx, nn * cin * h * wd), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)dx, (const __nv_bfloat16*)s.p[1], d, n0, nn, beta);
+    NK_LAUNCHED(ctx, "col2im");
+  }
+  ctx->last_conv_kernel = "tcgen05_im2col_gemm_dx";
+  return NK_OK;
+}
+
+int nk_conv_gemm_bwd_kernel(nk_ctx* ctx, void* dwt, int dw_dtype, const void* g, const void* x, int64_t n, int64_t cin, int64_t h,
+                            int64_t wd, int64_t cout, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t dh, int64_t dw,
+                            float beta) {
+  CgDims d;
+  if (!make_dims(d, n, cin, h, wd, cout, kh, kw, sh, sw, dh, dw) || !ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(g) & 15) return NK_ERR_UNSUPPORTED;
+  Scratch s(ctx);
+  const int64_t cs = chunk_samples(d);
+  int rc = nk_alloc_uninit(ctx, size_t(cs * d.L * d.Kp * 2), &s.p[1]);
+  if (rc) return rc;
+  rc = nk_alloc(ctx, size_t(cout * d.Kp * 4), &s.p[2]);   // f32 accumulator of the split reduction, zero filled
+  if (rc) return rc;
+  for (int64_t n0 = 0; n0 < n; n0 += cs) {
+    const int64_t nn = n - n0 < cs ? n - n0 : cs;
+    im2col_kernel<<<cg_blocks(ctx, nn * d.L * (d.Kp / 8)), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)s.p[1], (const __nv_bfloat16*)x, d, n0, nn);
+    NK_LAUNCHED(ctx, "im2col");
+    // acc (Cout x Kp) += sum_n G[n] (Cout x L) . cols[n] (L x Kp) : NN, reduced over the samples inside the k loop
+    rc = nk_gemm_tcgen05_batched(ctx, 0, 0, cout, d.Kp, d.L, 1.f, static_cast<const __nv_bfloat16*>(g) + n0 * cout * d.L, d.L,
+                                 cout * d.L, s.p[1], d.Kp, d.L * d.Kp, s.p[2], d.Kp, 0, nn, NK_F32, nullptr, NK_F32, 0, 1);
+    if (rc) return rc;
+  }
+  const int fb = int((cout * d.K + kThreads - 1) / kThreads);
+  if (dw_dtype == NK_BF16)
+    finalize_dw_padded<__nv_bfloat16><<<fb, kThreads, 0, ctx->stream>>>((__nv_bfloat16*)dwt, (const float*)s.p[2], cout, d.K, d.Kp, beta);
+  else
+    finalize_dw_padded<float><<<fb, kThreads, 0, ctx->stream>>>((float*)dwt, (const float*)s.p[2], cout, d.K, d.Kp, beta);
+  NK_LAUNCHED(ctx, "conv_dw_finalize_padded");
+  ctx->last_conv_kernel = "tcgen05_im2col_gemm_dw";
+  return NK_OK;
+}

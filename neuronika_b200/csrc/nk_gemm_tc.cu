@@ -37,6 +37,7 @@ struct GemmParams {
   const void* bias;
   float alpha, beta;
   int bias_bf16;
+  int bias_per_row;  // the bias is indexed by the output ROW (convolution: C rows are output channels) instead of the column
   int relu;
   const void* mask;    // optional (M, N) tensor of C's element type and leading dimension: v = mask > 0 ? v : 0 before the
                        // beta accumulate -- the ReLU backward of the layer below fused into the dX GEMM (relu/mod.rs:71-78)
@@ -49,6 +50,12 @@ struct GemmParams {
   int rs_world, m_rot;
   int64_t rs_rows;
   void* rs_dst[8];
+  // batched operation (im2col convolution, nk_gemm_batched): `batch` independent products whose operands are 3-D
+  // tensor maps (k, rows, batch); C of product b starts c_batch_stride elements further.  batch_reduce: ONE output,
+  // the products of all batches are summed (the k loop runs over (batch, k)); the batch range is split over
+  // `splits` CTAs per tile, which add their partial sums into C with f32 atomics (C zeroed / scaled by the host).
+  int batch, a_batched, b_batched, batch_reduce, splits;
+  int64_t c_batch_stride;
 };
 
 __device__ __forceinline__ int tile_m_block(const GemmParams& p, int tile) {
@@ -93,8 +100,16 @@ struct Cfg {
 
 template <typename TC>
 __device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int64_t row, int64_t col0, const uint32_t* r,
-                                                       int ncols, bool vec_ok) {
-  TC* crow = static_cast<TC*>(p.C) + row * p.ldc + col0;
+                                                       int ncols, bool vec_ok, int64_t c_off = 0, bool atomic = false) {
+  TC* crow = static_cast<TC*>(p.C) + c_off + row * p.ldc + col0;
+  if (atomic) {  // partial sum of a split reduction: f32 atomics (alpha applied, beta handled by the host)
+    if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols && col0 + j < p.N) atomicAdd(reinterpret_cast<float*>(crow) + j, p.alpha * __uint_as_float(r[j]));
+    }
+    return;
+  }
   if (p.rs_world) {
     const int owner = int(row / p.rs_rows);
     crow = static_cast<TC*>(p.rs_dst[owner]) + (row - owner * p.rs_rows) * p.ldc + col0;
@@ -103,7 +118,11 @@ __device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int6
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(r[j]);
   const bool full = (col0 + 32 <= p.N) && ncols == 32;
-  if (p.bias) {
+  if (p.bias && p.bias_per_row) {
+    const float b = p.bias_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[row]) : static_cast<const float*>(p.bias)[row];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += b;
+  } else if (p.bias) {
     // 32 scalar loads here serialise on L1 latency and made the epilogue slower than a K = 1024 main loop
     // (profiles/r01_launches.md): fetch the 32 bias values of a full chunk with 16-byte loads
     if (full && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
@@ -181,7 +200,7 @@ __device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int6
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, typename TC>
+template <int BLOCK_N, bool A_MN, bool B_MN, typename TC, bool BATCH = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
@@ -226,7 +245,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+  // BATCH: a "tile" is (batch or split, m block, n block); the k loop of a reducing launch walks its share of the batches
+  const int num_tiles = BATCH ? tiles_mn * (p.batch_reduce ? p.splits : p.batch) : tiles_mn;
+  auto batch_range = [&](int outer, int& b0, int& b1) {   // batches whose products tile `outer` accumulates
+    if (!p.batch_reduce) {
+      b0 = outer, b1 = outer + 1;
+    } else {
+      const int per = (p.batch + p.splits - 1) / p.splits;
+      b0 = outer * per;
+      b1 = min(p.batch, b0 + per);
+    }
+  };
 
   if (warp_idx == 0) {
     // ===================================================== TMA producer
@@ -234,9 +264,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int m_blk, n_blk;
-        tile_coords(p, tile, m_blk, n_blk);
+        int m_blk, n_blk, b0 = 0, b1 = 1;
+        tile_coords(p, BATCH ? tile % tiles_mn : tile, m_blk, n_blk);
+        if (BATCH) batch_range(tile / tiles_mn, b0, b1);
         const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        for (int bb = b0; bb < b1; ++bb)
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           ptx::mbar_expect_tx(full_bar(stage), C_::STAGE_BYTES);
@@ -245,17 +277,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint32_t sb = smem_b0 + stage * C_::B_BYTES;
           if (A_MN) {  // stored (K, M): boxes of 64 (m) x 64 (k)
 #pragma unroll
-            for (int c = 0; c < BLOCK_M / 64; ++c)
-              ptx::tma_load_2d(sa + c * (64 * BLOCK_K * 2), &tmap_a, full_bar(stage), m0 + c * 64, k0);
+            for (int c = 0; c < BLOCK_M / 64; ++c) {
+              if (BATCH && p.a_batched)
+                ptx::tma_load_3d(sa + c * (64 * BLOCK_K * 2), &tmap_a, full_bar(stage), m0 + c * 64, k0, bb);
+              else
+                ptx::tma_load_2d(sa + c * (64 * BLOCK_K * 2), &tmap_a, full_bar(stage), m0 + c * 64, k0);
+            }
           } else {  // stored (M, K): one box of 64 (k) x 128 (m)
-            ptx::tma_load_2d(sa, &tmap_a, full_bar(stage), k0, m0);
+            if (BATCH && p.a_batched)
+              ptx::tma_load_3d(sa, &tmap_a, full_bar(stage), k0, m0, bb);
+            else
+              ptx::tma_load_2d(sa, &tmap_a, full_bar(stage), k0, m0);
           }
           if (B_MN) {  // stored (K, N)
 #pragma unroll
-            for (int c = 0; c < BLOCK_N / 64; ++c)
-              ptx::tma_load_2d(sb + c * (64 * BLOCK_K * 2), &tmap_b, full_bar(stage), n0 + c * 64, k0);
+            for (int c = 0; c < BLOCK_N / 64; ++c) {
+              if (BATCH && p.b_batched)
+                ptx::tma_load_3d(sb + c * (64 * BLOCK_K * 2), &tmap_b, full_bar(stage), n0 + c * 64, k0, bb);
+              else
+                ptx::tma_load_2d(sb + c * (64 * BLOCK_K * 2), &tmap_b, full_bar(stage), n0 + c * 64, k0);
+            }
           } else {  // stored (N, K)
-            ptx::tma_load_2d(sb, &tmap_b, full_bar(stage), k0, n0);
+            if (BATCH && p.b_batched)
+              ptx::tma_load_3d(sb, &tmap_b, full_bar(stage), k0, n0, bb);
+            else
+              ptx::tma_load_2d(sb, &tmap_b, full_bar(stage), k0, n0);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -276,7 +322,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(as * BLOCK_N);
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        int k_total = p.num_k_blocks;
+        if (BATCH) {
+          int b0, b1;
+          batch_range(tile / tiles_mn, b0, b1);
+          k_total *= (b1 - b0);
+        }
+        for (int kb = 0; kb < k_total; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
           const uint64_t adesc = ptx::make_smem_desc_sw128(smem_a0 + stage * C_::A_BYTES, p.a_lbo, p.a_sbo);
@@ -308,7 +360,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
-      tile_coords(p, tile, m_blk, n_blk);
+      tile_coords(p, BATCH ? tile % tiles_mn : tile, m_blk, n_blk);
+      const int64_t c_off = (BATCH && !p.batch_reduce) ? int64_t(tile / tiles_mn) * p.c_batch_stride : 0;
+      const bool atomic = BATCH && p.batch_reduce;
       const int64_t row = int64_t(m_blk) * BLOCK_M + q * 32 + lane;
       ptx::mbar_wait(tmem_full_bar(as), aphase);
       ptx::tc_fence_after();
@@ -346,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               continue;
             }
           }
-          if (row < p.M && col0 < p.N) epilogue_store_chunk32<TC>(p, row, col0, r, 32, vec_ok);
+          if (row < p.M && col0 < p.N) epilogue_store_chunk32<TC>(p, row, col0, r, 32, vec_ok, c_off, atomic);
         }
       } else {
         uint32_t r[32];
@@ -356,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = j < 16 ? r16[j & 15] : 0u;
         const int64_t col0 = int64_t(n_blk) * BLOCK_N;
-        if (row < p.M && col0 < p.N) epilogue_store_chunk32<TC>(p, row, col0, r, 16, false);
+        if (row < p.M && col0 < p.N) epilogue_store_chunk32<TC>(p, row, col0, r, 16, false, c_off, atomic);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -401,18 +455,30 @@ uint32_t env_u32(const char* name, uint32_t dflt) {
   return v ? (uint32_t)strtoul(v, nullptr, 0) : dflt;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, typename TC>
+template <int BLOCK_N, bool A_MN, bool B_MN, typename TC, bool BATCH = false>
 int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p) {
   using C_ = Cfg<BLOCK_N>;
-  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, TC>;
-  static bool attr_done = false;  // per template instantiation
-  if (!attr_done) {
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, TC, BATCH>;
+  static bool attr_done[64] = {};  // per template instantiation and device (the attribute is per device)
+  if (!attr_done[ctx->device & 63]) {
     const uint32_t max_smem = C_::SMEM_BYTES + kRsStageBytes <= kSmemLimit ? C_::SMEM_BYTES + kRsStageBytes : C_::SMEM_BYTES;
     NK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-    attr_done = true;
+    attr_done[ctx->device & 63] = true;
   }
   p.num_n_blocks = int((p.N + BLOCK_N - 1) / BLOCK_N);
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  if (BATCH) {
+    if (p.batch_reduce) {
+      // split the batch range so that the launch fills the machine; every split gets at least one batch
+      int want = (ctx->sm_count + num_tiles - 1) / num_tiles;
+      if (want > p.batch) want = p.batch;
+      const int per = (p.batch + want - 1) / want;
+      p.splits = (p.batch + per - 1) / per;
+      num_tiles *= p.splits;
+    } else {
+      num_tiles *= p.batch;
+    }
+  }
   // persistent grid balanced over the waves the tiles need anyway: 512 tiles on 148 SMs take 4 waves whether 148
   // or 128 CTAs run them, and the 20 SMs left free let a concurrent NCCL all-reduce make progress
   const int waves = (num_tiles + ctx->sm_count - 1) / ctx->sm_count;
@@ -495,8 +561,10 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   p.alpha = alpha;
   p.beta = beta;
   p.bias_bf16 = bias_dtype == NK_BF16;
+  p.bias_per_row = 0;
   p.relu = relu;
   p.mask = mask;
+  p.batch = 1, p.a_batched = p.b_batched = p.batch_reduce = 0, p.splits = 1, p.c_batch_stride = 0;
   p.num_m_blocks = int((M + BLOCK_M - 1) / BLOCK_M);
   p.num_n_blocks = 0;
   p.num_k_blocks = int((K + BLOCK_K - 1) / BLOCK_K);
@@ -556,6 +624,77 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   if (a_mn && !b_mn) return NK_TC(true, false);
   return NK_TC(true, true);
 #undef NK_TC
+}
+
+// 3-D bf16 tensor map (cols, rows, batch)
+static int make_tmap_3d(nk_ctx* ctx, CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int64_t batch,
+                        int64_t batch_stride, uint32_t box_cols, uint32_t box_rows) {
+  if (!ctx->encode_tiled) return nk_set_error(ctx, NK_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)batch_stride * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return nk_set_error(ctx, NK_ERR_CUDA, "cuTensorMapEncodeTiled (3-d) failed (%d) rows=%lld cols=%lld ld=%lld batch=%lld stride=%lld",
+                        (int)r, (long long)rows, (long long)cols, (long long)ld, (long long)batch, (long long)batch_stride);
+  return NK_OK;
+}
+
+// `batch` products C_b = alpha * op(A_b).op(B_b) (+ row bias, ReLU) with operands batch_stride elements apart (stride 0 = the
+// same operand for every batch), or -- reduce != 0 -- ONE product C += alpha * sum_b op(A_b).op(B_b) (C f32, accumulated
+// with atomics: the caller zeroes / scales C first).  The engine behind the im2col convolution path (nk_conv_gemm.cu).
+// Returns NK_ERR_UNSUPPORTED (last_error untouched) when the operands are not TMA-addressable.
+int nk_gemm_tcgen05_batched(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
+                            int64_t lda, int64_t strideA, const void* B, int64_t ldb, int64_t strideB, void* C, int64_t ldc,
+                            int64_t strideC, int64_t batch, int c_dtype, const void* row_bias, int bias_dtype, int relu,
+                            int reduce) {
+  if (!nk_gemm_tcgen05_supported(transA, transB, M, N, K, A, lda, B, ldb)) return NK_ERR_UNSUPPORTED;
+  if (batch < 1 || batch > (int64_t(1) << 30) || (strideA * 2) % 16 != 0 || (strideB * 2) % 16 != 0) return NK_ERR_UNSUPPORTED;
+  if (reduce && c_dtype != NK_F32) return NK_ERR_UNSUPPORTED;
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  int block_n = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  GemmParams p;
+  p.M = M, p.N = N, p.K = K, p.ldc = ldc, p.C = C;
+  p.bias = row_bias, p.bias_bf16 = bias_dtype == NK_BF16, p.bias_per_row = 1;
+  p.alpha = alpha, p.beta = 0.f, p.relu = relu, p.mask = nullptr;
+  p.num_m_blocks = int((M + BLOCK_M - 1) / BLOCK_M);
+  p.num_n_blocks = 0;
+  p.num_k_blocks = int((K + BLOCK_K - 1) / BLOCK_K);
+  p.rs_world = 0, p.m_rot = 0, p.rs_rows = M;
+  for (int i = 0; i < 8; ++i) p.rs_dst[i] = nullptr;
+  p.batch = int(batch), p.a_batched = strideA != 0, p.b_batched = strideB != 0, p.batch_reduce = reduce ? 1 : 0, p.splits = 1;
+  p.c_batch_stride = strideC;
+  p.a_lbo = a_mn ? BLOCK_K * 128 : 16, p.a_sbo = 1024, p.a_kstep = a_mn ? UMMA_K * 128 : UMMA_K * 2;
+  p.b_lbo = b_mn ? BLOCK_K * 128 : 16, p.b_sbo = 1024, p.b_kstep = b_mn ? UMMA_K * 128 : UMMA_K * 2;
+  CUtensorMap ta, tb;
+  int rc;
+  if (p.a_batched)
+    rc = a_mn ? make_tmap_3d(ctx, &ta, A, K, M, lda, batch, strideA, 64, BLOCK_K)
+              : make_tmap_3d(ctx, &ta, A, M, K, lda, batch, strideA, BLOCK_K, BLOCK_M);
+  else
+    rc = a_mn ? make_tmap_2d(ctx, &ta, A, K, M, lda, 64, BLOCK_K) : make_tmap_2d(ctx, &ta, A, M, K, lda, BLOCK_K, BLOCK_M);
+  if (rc) return rc;
+  if (p.b_batched)
+    rc = b_mn ? make_tmap_3d(ctx, &tb, B, K, N, ldb, batch, strideB, 64, BLOCK_K)
+              : make_tmap_3d(ctx, &tb, B, N, K, ldb, batch, strideB, BLOCK_K, (uint32_t)block_n);
+  else
+    rc = b_mn ? make_tmap_2d(ctx, &tb, B, K, N, ldb, 64, BLOCK_K) : make_tmap_2d(ctx, &tb, B, N, K, ldb, BLOCK_K, (uint32_t)block_n);
+  if (rc) return rc;
+  ctx->last_gemm_kernel = "tcgen05_batched";
+#define NK_TCB(BN, AM, BM_)                                                                          \
+  (c_dtype == NK_BF16 ? launch_cfg<BN, AM, BM_, __nv_bfloat16, true>(ctx, ta, tb, p)                  \
+                      : launch_cfg<BN, AM, BM_, float, true>(ctx, ta, tb, p))
+#define NK_TCB_BN(AM, BM_) (block_n == 256 ? NK_TCB(256, AM, BM_) : block_n == 128 ? NK_TCB(128, AM, BM_) : NK_TCB(64, AM, BM_))
+  if (!a_mn && !b_mn) return NK_TCB_BN(false, false);
+  if (!a_mn && b_mn) return NK_TCB_BN(false, true);
+  if (a_mn && b_mn) return NK_TCB_BN(true, true);
+  return nk_set_error(ctx, NK_ERR_UNSUPPORTED, "batched gemm: the TT form is not instantiated");
+#undef NK_TCB_BN
+#undef NK_TCB
 }
 
 extern "C" {

@@ -723,3 +723,87 @@ def test_conv_backward_with_a_uniform_output_gradient(nk, dev, O):
     O.conv_backward_input(wx, gf, w, (1, 1), (1, 1))
     O.conv_backward_kernel(ww, gf, x, (1, 1), (1, 1))
     assert close(Xf.grad(), wx, rtol=1e-4, atol=1e-4) and close(Wf.grad(), ww, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("xs,cout,k,stride,dil", [((4, 32, 10, 18), 64, (3, 3), (1, 1), (1, 1)),
+                                                  ((8, 32, 34, 34), 64, (3, 3), (1, 1), (1, 1)),
+                                                  ((2, 3, 34, 34), 32, (3, 3), (1, 1), (1, 1)),
+                                                  ((2, 16, 17, 33), 24, (3, 3), (2, 2), (1, 1)),
+                                                  ((2, 8, 12, 20), 16, (3, 3), (1, 1), (2, 2)),
+                                                  ((3, 20, 9, 12), 136, (2, 5), (1, 1), (1, 1))])
+def test_conv2d_im2col_gemm_engine(nk, dev, O, xs, cout, k, stride, dil):
+    """every bf16, groups = 1 convolution the two specialised kernels do not take runs as im2col + batched tcgen05 GEMM
+    (forward with bias + ReLU in the epilogue, dX through col2im, dW as a split reduction over the samples): config 5's
+    32 -> 64 layer, strides, dilations, Cout not a multiple of 128, K not a multiple of 8"""
+    from neuronika_b200 import ops
+    rng = np.random.default_rng(sum(xs) + cout)
+    x = O.bf16_round(rng.uniform(-1, 1, xs).astype(F32))
+    w = O.bf16_round(rng.uniform(-0.2, 0.2, (cout, xs[1]) + k).astype(F32))
+    b = O.bf16_round(rng.uniform(-0.2, 0.2, (cout,)).astype(F32))
+    X, W, B = dev.from_ndarray(x, nk.BF16), dev.from_ndarray(w, nk.BF16), dev.from_ndarray(b, nk.BF16)
+    y = ops.conv2d(X, W, stride, dil)
+    assert dev.last_conv_kernel == "tcgen05_im2col_gemm_fwd"
+    want = O.conv_forward(x, w, stride, dil).astype(np.float64)
+    scale = float(np.sqrt((want ** 2).mean())) + 1e-9
+    assert np.all(np.abs(y.as_ndarray() - want) <= 2e-3 * scale + 2.0 ** -8 * np.abs(want))
+    yb = ops.conv2d(X, W, stride, dil, bias=B, relu=True)
+    wb = np.maximum(want + b[None, :, None, None], 0)
+    assert np.all(np.abs(yb.as_ndarray() - wb) <= 2e-3 * scale + 2.0 ** -8 * np.abs(wb))
+    g = O.bf16_round(rng.uniform(-1, 1, want.shape).astype(F32))
+    G = dev.from_ndarray(g, nk.BF16)
+    dx0 = O.bf16_round(rng.uniform(-1, 1, xs).astype(F32))
+    dw0 = rng.uniform(-1, 1, w.shape).astype(F32)
+    for beta in (0.0, 1.0):
+        dx, dw, db = dev.from_ndarray(dx0, nk.BF16), dev.from_ndarray(dw0, nk.F32), dev.zeros((cout, 1, 1), nk.F32)
+        ops.conv2d_bwd_input(dx, G, W, stride, dil, beta=beta)
+        # (3x3 kernels on <= 3 input channels have their own backward kernels; everything else is the GEMM engine)
+        thin = xs[1] <= 3 and k == (3, 3) and stride == (1, 1) and dil == (1, 1)
+        assert dev.last_conv_kernel == ("tcgen05_implicit_gemm_dx" if thin else "tcgen05_im2col_gemm_dx")
+        ops.conv2d_bwd_kernel(dw, G, X, stride, dil, beta=beta, dbias=db)
+        assert dev.last_conv_kernel.startswith("tcgen05")
+        wx = (dx0 if beta else np.zeros_like(x)).astype(np.float64)
+        ww = (dw0 if beta else np.zeros_like(w)).copy()
+        gx = np.zeros_like(x)
+        O.conv_backward_input(gx, g, w, stride, dil)
+        O.conv_backward_kernel(ww, g, x, stride, dil)
+        wx = wx + gx
+        sx = float(np.sqrt((gx.astype(np.float64) ** 2).mean())) + 1e-9
+        # dX: the column gradients are rounded to bf16 before col2im sums up to kh*kw of them
+        assert np.all(np.abs(dx.as_ndarray() - wx) <= 1.5e-2 * sx + 2.0 ** -7 * np.abs(wx)), beta
+        sw_ = float(np.sqrt(((ww - (dw0 if beta else 0)) ** 2).mean())) + 1e-9
+        assert np.all(np.abs(dw.as_ndarray() - ww) <= 2e-3 * sw_ + 1e-5 * np.abs(ww)), beta
+        assert np.allclose(db.as_ndarray().ravel(), g.astype(np.float64).sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
+
+
+def test_small_convnet_runs_on_tensor_cores(nk, dev, O):
+    """config 5's shape of network (Conv2d 3->32 p1, Conv2d 32->64 p1, Linear) at a small batch: every convolution kernel
+    of forward and backward is a tcgen05 one, and the step matches the oracle"""
+    rng = np.random.default_rng(81)
+    n = 16
+    x = O.bf16_round(rng.uniform(0, 1, (n, 3, 32, 32)).astype(F32))
+    w1 = O.bf16_round(rng.uniform(-0.2, 0.2, (32, 3, 3, 3)).astype(F32))
+    w2 = O.bf16_round(rng.uniform(-0.06, 0.06, (64, 32, 3, 3)).astype(F32))
+    X = nk.from_ndarray(dev, x, nk.BF16)
+    W1 = nk.from_ndarray(dev, w1, nk.BF16).requires_grad(nk.F32)
+    W2 = nk.from_ndarray(dev, w2, nk.BF16).requires_grad(nk.F32)
+    seen = []
+    h1 = W1.convolution(X.pad((1, 1)), (1, 1), (1, 1), 1).relu()
+    h2 = W2.convolution(h1.pad((1, 1)), (1, 1), (1, 1), 1).relu()
+    loss = h2.mean()
+    loss.forward()
+    seen.append(dev.last_conv_kernel)
+    loss.backward(1.0)
+    seen.append(dev.last_conv_kernel)
+    assert all(s.startswith("tcgen05") for s in seen), seen
+    # oracle
+    xp = O.pad_forward(x, (1, 1))
+    a1 = O.conv_forward(xp, w1, (1, 1), (1, 1))
+    h1o = O.bf16_round(O.relu_forward(O.bf16_round(a1)))
+    a2 = O.conv_forward(O.pad_forward(h1o, (1, 1)), w2, (1, 1), (1, 1))
+    h2o = O.relu_forward(O.bf16_round(a2))
+    assert abs(loss.item() - float(h2o.mean(dtype=np.float64))) <= 2e-3 * float(np.abs(h2o).mean()) + 1e-6
+    g2 = O.bf16_round(np.full(h2o.shape, 1.0 / h2o.size, F32)) * (O.bf16_round(a2) > 0)
+    dw2 = np.zeros_like(w2)
+    O.conv_backward_kernel(dw2, g2.astype(F32), O.pad_forward(h1o, (1, 1)), (1, 1), (1, 1))
+    got = W2.grad()
+    assert np.all(np.abs(got - dw2) <= 2e-2 * np.abs(dw2).max())
