@@ -655,7 +655,9 @@ def test_fusion_level_2_relu_backward_in_the_gemm_epilogue(nk, dev, O):
     assert grads[2][1] <= grads[1][1] - 1
     assert grads[1][2] == grads[2][2]
     for i, (a, b) in enumerate(zip(grads[1][0], grads[2][0])):
-        if a.ndim == 1:      # bias gradients: column sums with f32 atomics (order varies from launch to launch)
+        # bias gradients (column sums) and the 10-row dW of the output layer (gemm_small_m_kernel) are accumulated with
+        # f32 atomics, whose order varies from launch to launch: equal to rounding.  Everything else is bit equal.
+        if a.ndim == 1 or a.shape[0] <= 16:
             assert np.allclose(a, b, rtol=1e-4, atol=1e-7), i
         else:
             assert np.array_equal(a, b), i

@@ -37,7 +37,7 @@ def traffic_json(tag, workloads):
             out["gemm_tc_4096"] = {"bytes_per_launch": sum(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"] for k in g) / max(len(g), 1),
                                    "launches": len(g)}
         if w == "conv":
-            for key, pat in (("conv_fwd_tc", "conv_fwd_tc_kernel"), ("conv_bwd_fused_tc", "conv_bwd_fused_kernel")):
+            for key, pat in (("conv_fwd_tc", "conv_fwd_t"), ("conv_bwd_fused_tc", "conv_bwd_fused_kernel")):
                 g = [k for k in last if pat in k["name"]]
                 if g:
                     out[key] = {"bytes_per_launch": sum(k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"] for k in g) / len(g),
