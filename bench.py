@@ -661,7 +661,10 @@ def exchange_parity(env, wl):
     NCCL all-reduce of the local bucket: the two buckets must agree (bit for bit at two ranks, where a + b is order
     independent; to rounding otherwise -- the owner sums in rank order, NCCL in ring order)."""
     torch, dist, stream = env.torch, env.dist, env.stream
-    wl.full_step(wl.step_resident, wl.sets[0])
+    # compute + exchange WITHOUT the optimizer step: the SGD kernel scales the bucket by 1/world in place and moves the
+    # weights, so a comparison after a full step would compare different things
+    wl.step_resident(wl.sets[0])
+    wl.sync.wait()
     stream.synchronize()
     fused = wl.bucket.as_torch().clone()
     wl.fused.detach()

@@ -50,6 +50,9 @@ typedef enum { NK_F32 = 0, NK_BF16 = 1 } nk_dtype;
 /* GEMM engine selection (nk_gemm_config): AUTO picks tcgen05 whenever the operands are
  * bf16 and TMA-addressable, else the SIMT kernel. */
 typedef enum { NK_GEMM_AUTO = 0, NK_GEMM_SIMT = 1, NK_GEMM_TCGEN05 = 2 } nk_gemm_engine;
+/* Convolution engine selection (nk_conv_config): AUTO = tensor-core kernels wherever they apply; DIRECT = the CUDA-core
+ * kernels only (the parity path the reference's goldens run on); UNFUSED = AUTO without the one-pass dX + dW backward. */
+typedef enum { NK_CONV_AUTO = 0, NK_CONV_DIRECT = 1, NK_CONV_UNFUSED = 2 } nk_conv_engine;
 
 /* ---- context (replaces cuda::Device, neuronika-variable/src/cuda/device.rs:11-75) ---- */
 int nk_ctx_create(int device, nk_ctx** out);
@@ -64,6 +67,7 @@ int nk_sync(nk_ctx* ctx);
 uint64_t nk_launch_count(nk_ctx* ctx);
 int nk_sm_count(nk_ctx* ctx);
 int nk_gemm_config(nk_ctx* ctx, int engine /* nk_gemm_engine */);
+int nk_conv_config(nk_ctx* ctx, int engine /* nk_conv_engine */);
 /* name of the kernel variant the last nk_gemm call used ("tcgen05_nt_128x256", "simt", ...) */
 const char* nk_last_gemm_kernel(nk_ctx* ctx);
 

@@ -193,14 +193,14 @@ int nk_conv2d_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const void
   if (total == 0) return NK_OK;
   NK_REQUIRE(ctx, y && x && w, "nk_conv2d_fwd: NULL pointer");
   if (dtype == NK_BF16 && sh == 1 && sw == 1 && dh == 1 && dw == 1 && groups == 1) {
-    if (conv_engine_override() != 1 && !getenv("NK_CONV_DIRECT") && nk_conv_tz_supported(n, cin, h, wd, cout, kh, kw, x, y)) {
+    if (conv_engine_override() != 1 && ctx->conv_engine != NK_CONV_DIRECT && nk_conv_tz_supported(n, cin, h, wd, cout, kh, kw, x, y)) {
       rc = nk_conv_tz_fwd(ctx, y, x, w, bias, relu, n, cin, h, wd, cout, kh, kw);
       if (rc != NK_ERR_UNSUPPORTED) return rc;
     }
     rc = nk_conv2d_fwd_tc(ctx, y, x, w, bias, relu, n, cin, h, wd, cout, kh, kw);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }
-  if (dtype == NK_BF16 && groups == 1 && !getenv("NK_CONV_DIRECT")) {
+  if (dtype == NK_BF16 && groups == 1 && ctx->conv_engine != NK_CONV_DIRECT) {
     rc = nk_conv_gemm_fwd(ctx, y, x, w, bias, relu, n, cin, h, wd, cout, kh, kw, sh, sw, dh, dw);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }
@@ -229,7 +229,7 @@ int nk_conv2d_bwd_input(nk_ctx* ctx, void* dx, const void* g, const void* w, int
     rc = nk_conv2d_bwd_input_tc(ctx, dx, g, w, n, cin, h, wd, cout, kh, kw, beta);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }
-  if (dtype == NK_BF16 && groups == 1 && !getenv("NK_CONV_DIRECT")) {
+  if (dtype == NK_BF16 && groups == 1 && ctx->conv_engine != NK_CONV_DIRECT) {
     rc = nk_conv_gemm_bwd_input(ctx, dx, g, w, n, cin, h, wd, cout, kh, kw, sh, sw, dh, dw, beta);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }
@@ -258,7 +258,7 @@ int nk_conv2d_bwd_kernel(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, cons
     rc = nk_conv2d_bwd_kernel_tc(ctx, dwt, dw_dtype, dbias, g, x, n, cin, h, wd, cout, kh, kw, beta);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }
-  if (dtype == NK_BF16 && groups == 1 && !getenv("NK_CONV_DIRECT")) {
+  if (dtype == NK_BF16 && groups == 1 && ctx->conv_engine != NK_CONV_DIRECT) {
     rc = nk_conv_gemm_bwd_kernel(ctx, dwt, dw_dtype, g, x, n, cin, h, wd, cout, kh, kw, sh, sw, dh, dw, beta);
     if (rc == NK_OK && dbias) {
       int64_t dshape[3] = {d.cout, 1, 1};

@@ -5,8 +5,10 @@
 // split reduction over the samples inside the GEMM's k loop.  It takes every bf16 shape the two specialised engines
 // (nk_conv_tz.cu: thin inputs; nk_conv_tc.cu: 3x3 with Cin <= 3 backward) do not, e.g. config 5's 32 -> 64 layer;
 // only shapes TMA cannot address (Ho*Wo not a multiple of 8) fall through to the CUDA-core kernels.
-//   cols[n][l][k]  k = (c, i, j) as in the reference (utils.rs:332-353), padded with zeros to Kp = ceil8(K) so that rows
-//   are 16-byte multiples (TMA); the buffer lives in HBM for the duration of the call (sample chunks of <= 4 GB).
+//   colsT[n][k][l]  k = (c, i, j) as in the reference (utils.rs:332-353), l = output pixel: the TRANSPOSE of the
+//   reference's (l, k) column matrix, so that a row is a shifted copy of image rows (im2col / col2im move contiguous
+//   runs) and is the MN-major UMMA operand as it lies; the buffer lives in HBM for the duration of the call (sample
+//   chunks of <= 4 GB).  The (Cout, K) kernel is copied once into rows of Kp = ceil8(K) elements (TMA row pitch).
 // Compute bound for Cin >= 16 (K >= 144); the column buffer adds 2 x |cols| of HBM traffic.
 #include "nk_internal.cuh"
 
@@ -24,54 +26,84 @@ struct CgDims {
   int64_t n, cin, h, w, cout, kh, kw, sh, sw, dh, dw, ho, wo, K, Kp, L;
 };
 
-// cols[n][l][k8 .. k8+7]: one thread per 16-byte vector
+// colsT[ns][k][l0 .. l0+7]: one thread per 16-byte vector of eight consecutive output pixels of one im2col row
+// k = (c, i, j).  With a unit horizontal stride the eight values are a contiguous (2-byte aligned) run of the image row:
+// aligned 4-byte loads + a funnel shift when the run starts on an odd element; every store is a full 16-byte vector and a
+// warp writes 512 contiguous bytes, so the kernel runs at copy speed (the first version gathered element by element into
+// a k-contiguous buffer: 6.4 ms for config 5's 2.35 GB, profiles/r02_launches.md).
 __global__ void __launch_bounds__(kThreads) im2col_kernel(__nv_bfloat16* __restrict__ cols, const __nv_bfloat16* __restrict__ x,
                                                           CgDims d, int64_t n0, int64_t nn) {
-  const int64_t kv = d.Kp / 8;
-  const int64_t total = nn * d.L * kv;
+  const uint32_t lv_n = uint32_t(d.L / 8), K = uint32_t(d.K), wo = uint32_t(d.wo), kw = uint32_t(d.kw), kh = uint32_t(d.kh);
+  const int64_t total = nn * int64_t(K) * lv_n;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int64_t x_elems = d.n * d.cin * d.h * d.w;
   for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int64_t v = idx % kv, l = (idx / kv) % d.L, ns = idx / (kv * d.L);
-    const int64_t p = l / d.wo, q = l - p * d.wo;
-    const __nv_bfloat16* xs = x + (n0 + ns) * d.cin * d.h * d.w;
-    __align__(16) __nv_bfloat16 out[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int64_t k = v * 8 + e;
-      if (k < d.K) {
-        const int64_t j = k % d.kw, i = (k / d.kw) % d.kh, c = k / (d.kw * d.kh);
-        out[e] = xs[(c * d.h + p * d.sh + i * d.dh) * d.w + q * d.sw + j * d.dw];
+    const uint32_t row = uint32_t(idx / lv_n);          // (ns, k)
+    const uint32_t lv = uint32_t(idx - int64_t(row) * lv_n);
+    const uint32_t ns = row / K, k = row - ns * K;
+    const uint32_t j = k % kw, ci = k / kw, i = ci % kh, c = ci / kh;
+    const uint32_t l0 = lv * 8, p = l0 / wo, q = l0 - p * wo;
+    const int64_t plane = ((n0 + ns) * d.cin + c) * d.h;
+    uint4 out;
+    if (d.sw == 1 && q + 8 <= wo) {
+      const int64_t off = (plane + p * d.sh + i * d.dh) * d.w + q + j * d.dw;   // first of 8 consecutive source elements
+      const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
+      if ((off & 1) == 0) {
+        const uint32_t* s = xw + (off >> 1);
+        out = make_uint4(__ldg(s), __ldg(s + 1), __ldg(s + 2), __ldg(s + 3));
       } else {
-        out[e] = __float2bfloat16_rn(0.f);
+        const uint32_t* s = xw + ((off - 1) >> 1);
+        const uint32_t w0 = __ldg(s), w1 = __ldg(s + 1), w2 = __ldg(s + 2), w3 = __ldg(s + 3);
+        // the fifth word holds source element off+7 in its low half; its high half may lie past the end of x
+        const uint32_t w4 = (off + 9 <= x_elems) ? __ldg(s + 4)
+                                                 : uint32_t(reinterpret_cast<const unsigned short*>(x)[off + 7]);
+        out = make_uint4(__funnelshift_r(w0, w1, 16), __funnelshift_r(w1, w2, 16), __funnelshift_r(w2, w3, 16),
+                         __funnelshift_r(w3, w4, 16));
       }
+    } else {
+      __align__(16) unsigned short e[8];
+      const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const uint32_t l = l0 + t, pp = l / wo, qq = l - pp * wo;
+        e[t] = __ldg(xs + (plane + pp * d.sh + i * d.dh) * d.w + qq * d.sw + j * d.dw);
+      }
+      out = *reinterpret_cast<const uint4*>(e);
     }
-    *reinterpret_cast<uint4*>(cols + idx * 8) = *reinterpret_cast<const uint4*>(out);
+    reinterpret_cast<uint4*>(cols)[idx] = out;
   }
 }
 
-// dx[n,c,u,v] = beta*dx + sum_{i,j : u = p*sh + i*dh, v = q*sw + j*dw} dcols[n][p*wo+q][(c,i,j)]
+// dx[n,c,u,v] = beta*dx + sum_{i,j : u = p*sh + i*dh, v = q*sw + j*dw} dcolsT[ns][(c,i,j)][p*wo+q]
+// one thread per dx element; for a fixed tap the reads of a warp are consecutive pixels of one dcolsT row (coalesced)
 __global__ void __launch_bounds__(kThreads) col2im_kernel(__nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ dcols,
                                                           CgDims d, int64_t n0, int64_t nn, float beta) {
   const int64_t total = nn * d.cin * d.h * d.w;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int w = int(d.w), h = int(d.h), cin = int(d.cin), kh = int(d.kh), kw = int(d.kw), sh = int(d.sh), sw = int(d.sw),
+            dh = int(d.dh), dw = int(d.dw), ho = int(d.ho), wo = int(d.wo);
+  const uint32_t hw = uint32_t(h) * uint32_t(w);
   for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int64_t v = idx % d.w, u = (idx / d.w) % d.h, c = (idx / (d.w * d.h)) % d.cin, ns = idx / (d.w * d.h * d.cin);
-    const __nv_bfloat16* dc = dcols + ns * d.L * d.Kp;
+    const uint32_t pl = uint32_t(idx / hw);             // (ns, c)
+    const uint32_t uv = uint32_t(idx - int64_t(pl) * hw);
+    const int u = int(uv / uint32_t(w)), v = int(uv) - u * w;
+    const uint32_t ns = pl / uint32_t(cin), c = pl - ns * uint32_t(cin);
+    const __nv_bfloat16* dc = dcols + (int64_t(ns) * d.K + int64_t(c) * kh * kw) * d.L;
     float acc = 0.f;
-    for (int64_t i = 0; i < d.kh; ++i) {
-      const int64_t pu = u - i * d.dh;
-      if (pu < 0 || pu % d.sh != 0) continue;
-      const int64_t p = pu / d.sh;
-      if (p >= d.ho) continue;
-      for (int64_t j = 0; j < d.kw; ++j) {
-        const int64_t qv = v - j * d.dw;
-        if (qv < 0 || qv % d.sw != 0) continue;
-        const int64_t q = qv / d.sw;
-        if (q >= d.wo) continue;
-        acc += __bfloat162float(dc[(p * d.wo + q) * d.Kp + (c * d.kh + i) * d.kw + j]);
+    for (int i = 0; i < kh; ++i) {
+      const int pu = u - i * dh;
+      if (pu < 0) break;
+      const int p = pu / sh;
+      if (p * sh != pu || p >= ho) continue;
+      for (int j = 0; j < kw; ++j) {
+        const int qv = v - j * dw;
+        if (qv < 0) break;
+        const int q = qv / sw;
+        if (q * sw != qv || q >= wo) continue;
+        acc += __bfloat162float(dc[int64_t(i * kw + j) * d.L + p * wo + q]);
       }
     }
-    __nv_bfloat16* o = dx + (n0 + ns) * d.cin * d.h * d.w + (idx - ns * d.cin * d.h * d.w);
+    __nv_bfloat16* o = dx + n0 * d.cin * d.h * d.w + idx;
     if (beta != 0.f) acc += beta * __bfloat162float(*o);
     *o = __float2bfloat16_rn(acc);
   }
@@ -143,7 +175,7 @@ int nk_conv_gemm_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const v
                      int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw, int64_t sh, int64_t sw, int64_t dh, int64_t dw) {
   CgDims d;
   if (!make_dims(d, n, cin, h, wd, cout, kh, kw, sh, sw, dh, dw) || !ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(y) & 15) || cout < 8) return NK_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(x) & 3) || cout < 8) return NK_ERR_UNSUPPORTED;
   Scratch s(ctx);
   int rc = nk_alloc_uninit(ctx, size_t(cout * d.Kp * 2), &s.p[0]);
   if (rc) return rc;
@@ -154,10 +186,10 @@ int nk_conv_gemm_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const v
   if (rc) return rc;
   for (int64_t n0 = 0; n0 < n; n0 += cs) {
     const int64_t nn = n - n0 < cs ? n - n0 : cs;
-    im2col_kernel<<<cg_blocks(ctx, nn * d.L * (d.Kp / 8)), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)s.p[1], (const __nv_bfloat16*)x, d, n0, nn);
+    im2col_kernel<<<cg_blocks(ctx, nn * d.K * (d.L / 8)), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)s.p[1], (const __nv_bfloat16*)x, d, n0, nn);
     NK_LAUNCHED(ctx, "im2col");
-    // y[n] (Cout x L) = Wp (Cout x Kp) . cols[n]^T : NT, A shared by every sample
-    rc = nk_gemm_tcgen05_batched(ctx, 0, 1, cout, d.L, d.Kp, 1.f, s.p[0], d.Kp, 0, s.p[1], d.Kp, d.L * d.Kp,
+    // y[n] (Cout x L) = Wp (Cout x K) . colsT[n] (K x L) : NN, A shared by every sample (TMA zero-fills k >= K)
+    rc = nk_gemm_tcgen05_batched(ctx, 0, 0, cout, d.L, d.K, 1.f, s.p[0], d.Kp, 0, s.p[1], d.L, d.K * d.L,
                                  static_cast<__nv_bfloat16*>(y) + n0 * cout * d.L, d.L, cout * d.L, nn, NK_BF16, bias, NK_BF16,
                                  relu, 0);
     if (rc) return rc;
@@ -181,9 +213,10 @@ int nk_conv_gemm_bwd_input(nk_ctx* ctx, void* dx, const void* g, const void* w, 
   if (rc) return rc;
   for (int64_t n0 = 0; n0 < n; n0 += cs) {
     const int64_t nn = n - n0 < cs ? n - n0 : cs;
-    // dcols[n] (L x Kp) = G[n]^T (L x Cout) . Wp (Cout x Kp) : TN (A = G[n] stored (Cout, L)), B shared
-    rc = nk_gemm_tcgen05_batched(ctx, 1, 0, d.L, d.Kp, cout, 1.f, static_cast<const __nv_bfloat16*>(g) + n0 * cout * d.L, d.L,
-                                 cout * d.L, s.p[0], d.Kp, 0, s.p[1], d.Kp, d.L * d.Kp, nn, NK_BF16, nullptr, NK_BF16, 0, 0);
+    // dcolsT[n] (K x L) = Wp^T (K x Cout) . G[n] (Cout x L) : TN (A = Wp stored (Cout, K), shared), B = G[n] as stored
+    rc = nk_gemm_tcgen05_batched(ctx, 1, 0, d.K, d.L, cout, 1.f, s.p[0], d.Kp, 0,
+                                 static_cast<const __nv_bfloat16*>(g) + n0 * cout * d.L, d.L, cout * d.L, s.p[1], d.L, d.K * d.L, nn,
+                                 NK_BF16, nullptr, NK_BF16, 0, 0);
     if (rc) return rc;
     col2im_kernel<<<cg_blocks(ctx, nn * cin * h * wd), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)dx, (const __nv_bfloat16*)s.p[1], d, n0, nn, beta);
     NK_LAUNCHED(ctx, "col2im");
@@ -197,7 +230,7 @@ int nk_conv_gemm_bwd_kernel(nk_ctx* ctx, void* dwt, int dw_dtype, const void* g,
                             float beta) {
   CgDims d;
   if (!make_dims(d, n, cin, h, wd, cout, kh, kw, sh, sw, dh, dw) || !ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
-  if (reinterpret_cast<uintptr_t>(g) & 15) return NK_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(g) & 15) || (reinterpret_cast<uintptr_t>(x) & 3)) return NK_ERR_UNSUPPORTED;
   Scratch s(ctx);
   const int64_t cs = chunk_samples(d);
   int rc = nk_alloc_uninit(ctx, size_t(cs * d.L * d.Kp * 2), &s.p[1]);
@@ -206,11 +239,11 @@ int nk_conv_gemm_bwd_kernel(nk_ctx* ctx, void* dwt, int dw_dtype, const void* g,
   if (rc) return rc;
   for (int64_t n0 = 0; n0 < n; n0 += cs) {
     const int64_t nn = n - n0 < cs ? n - n0 : cs;
-    im2col_kernel<<<cg_blocks(ctx, nn * d.L * (d.Kp / 8)), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)s.p[1], (const __nv_bfloat16*)x, d, n0, nn);
+    im2col_kernel<<<cg_blocks(ctx, nn * d.K * (d.L / 8)), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)s.p[1], (const __nv_bfloat16*)x, d, n0, nn);
     NK_LAUNCHED(ctx, "im2col");
-    // acc (Cout x Kp) += sum_n G[n] (Cout x L) . cols[n] (L x Kp) : NN, reduced over the samples inside the k loop
-    rc = nk_gemm_tcgen05_batched(ctx, 0, 0, cout, d.Kp, d.L, 1.f, static_cast<const __nv_bfloat16*>(g) + n0 * cout * d.L, d.L,
-                                 cout * d.L, s.p[1], d.Kp, d.L * d.Kp, s.p[2], d.Kp, 0, nn, NK_F32, nullptr, NK_F32, 0, 1);
+    // acc (Cout x K) += sum_n G[n] (Cout x L) . colsT[n]^T (L x K) : NT, reduced over the samples inside the k loop
+    rc = nk_gemm_tcgen05_batched(ctx, 0, 1, cout, d.K, d.L, 1.f, static_cast<const __nv_bfloat16*>(g) + n0 * cout * d.L, d.L,
+                                 cout * d.L, s.p[1], d.L, d.K * d.L, s.p[2], d.Kp, 0, nn, NK_F32, nullptr, NK_F32, 0, 1);
     if (rc) return rc;
   }
   const int fb = int((cout * d.K + kThreads - 1) / kThreads);

@@ -431,7 +431,7 @@ int make_x_tmap(nk_ctx* ctx, CUtensorMap* tm, const void* x, int64_t n, int64_t 
 
 int nk_conv2d_fwd_tc(nk_ctx* ctx, void* y, const void* x, const void* w, const void* bias, int relu, int64_t n,
                      int64_t cin, int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw) {
-  if (getenv("NK_CONV_DIRECT")) return NK_ERR_UNSUPPORTED;
+  if (ctx->conv_engine == NK_CONV_DIRECT) return NK_ERR_UNSUPPORTED;
   if (!ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
   // TMA addressing: 16-byte aligned base, every global stride a multiple of 16 bytes  => W % 8 == 0
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (wd % 8) != 0) return NK_ERR_UNSUPPORTED;
@@ -470,13 +470,13 @@ int nk_conv2d_fwd_tc(nk_ctx* ctx, void* y, const void* x, const void* w, const v
   if (make_x_tmap(ctx, &tm, x, n, cin, h, wd, 64, p.kh, p.cpg, true) != NK_OK) return NK_ERR_UNSUPPORTED;
   if (make_x_tmap(ctx, &tmh, x, n, cin, h, wd, 8, p.kh, p.cpg, false) != NK_OK) return NK_ERR_UNSUPPORTED;
 
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // the attribute is per device
+  if (!attr_done[ctx->device & 63]) {
     NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     NK_CUDA(ctx, cudaFuncSetAttribute(conv_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_done = true;
+    attr_done[ctx->device & 63] = true;
   }
   const int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
   if (bias && relu)
@@ -781,7 +781,7 @@ __global__ void conv_dw_finalize(T* __restrict__ dw, T* __restrict__ dbias, cons
 int nk_conv2d_bwd_kernel_tc(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, const void* g, const void* x,
                             int64_t n, int64_t cin, int64_t h, int64_t wd, int64_t cout, int64_t kh, int64_t kw,
                             float beta) {
-  if (getenv("NK_CONV_DIRECT")) return NK_ERR_UNSUPPORTED;
+  if (ctx->conv_engine == NK_CONV_DIRECT) return NK_ERR_UNSUPPORTED;
   if (!ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (wd % 8) != 0) return NK_ERR_UNSUPPORTED;
   if (kh > 16 || kh < 1 || kw < 1 || kw > 8 || cout > 128 || cout < 1 || n > 65535) return NK_ERR_UNSUPPORTED;
@@ -837,10 +837,10 @@ int nk_conv2d_bwd_kernel_tc(nk_ctx* ctx, void* dwt, int dw_dtype, void* dbias, c
     p.scratch = scratch;
   }
   NK_CUDA(ctx, cudaMemsetAsync(scratch, 0, size_t(128) * p.ncols * sizeof(float), ctx->stream));
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // the attribute is per device
+  if (!attr_done[ctx->device & 63]) {
     NK_CUDA(ctx, cudaFuncSetAttribute(conv_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_done = true;
+    attr_done[ctx->device & 63] = true;
   }
   const size_t smem = 1024 + size_t(p.stages) * stage_bytes + 512 + 16384;
   conv_dw_tc_kernel<<<grid, kWThreads, smem, ctx->stream>>>(tm, tmh, p);
@@ -1131,10 +1131,10 @@ __global__ void __launch_bounds__(kXThreads, 1) conv_dx_tc_kernel(const ConvXP p
 template <int CIN>
 int launch_dx(nk_ctx* ctx, const ConvXP& p, int grid, size_t smem) {
   auto kern = conv_dx_tc_kernel<CIN, 3, 3>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // the attribute is per device
+  if (!attr_done[ctx->device & 63]) {
     NK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_done = true;
+    attr_done[ctx->device & 63] = true;
   }
   kern<<<grid, kXThreads, smem, ctx->stream>>>(p);
   NK_LAUNCHED(ctx, "conv_dx_tc");
@@ -1145,7 +1145,7 @@ int launch_dx(nk_ctx* ctx, const ConvXP& p, int grid, size_t smem) {
 
 int nk_conv2d_bwd_input_tc(nk_ctx* ctx, void* dx, const void* g, const void* w, int64_t n, int64_t cin, int64_t h,
                            int64_t wd, int64_t cout, int64_t kh, int64_t kw, float beta) {
-  if (getenv("NK_CONV_DIRECT")) return NK_ERR_UNSUPPORTED;
+  if (ctx->conv_engine == NK_CONV_DIRECT) return NK_ERR_UNSUPPORTED;
   if (kh != 3 || kw != 3 || cin < 1 || cin > 3) return NK_ERR_UNSUPPORTED;       // (c,i,j) rows <= 32 TMEM lanes
   if (cout % 16 != 0 || cout > 128 || wd > 256 || n > (1 << 20)) return NK_ERR_UNSUPPORTED;
   ConvXP p;
@@ -1266,12 +1266,23 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           0x3F803F80u;
     }
   }
+  if (p.use_const) {
+    // uniform output gradient: the G tile is the same for every row -- written ONCE into every stage (value inside the
+    // row, zero beyond Wo), never fetched and never rewritten; the loader warps have nothing to do per row
+    for (int i = threadIdx.x; i < S * kChunksPerTile * p.cout * 32; i += kFThreads) {
+      const int wq = i & 31, o = (i >> 5) % p.cout, sc = (i >> 5) / p.cout;
+      const int s = sc / kChunksPerTile, c = sc % kChunksPerTile;
+      const uint32_t val = (p.wo - c * kChunk - wq * 2) > 0 ? p.const_bits : 0u;
+      *reinterpret_cast<uint32_t*>(base_ptr + st_off + s * stage_bytes + c * chunk_bytes + o * 128 +
+                                   ((((wq >> 2) ^ (o & 7)) << 4) + (wq & 3) * 4)) = val;
+    }
+  }
   if (warp_idx == 1 && lane == 0) {
     ptx::prefetch_tmap(&tmap_x);
     ptx::prefetch_tmap(&tmap_halo);
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(fullx_bar(s), 1);
-      ptx::mbar_init(ready_bar(s), 256 + 4);
+      ptx::mbar_init(ready_bar(s), p.use_const ? 4 : 256 + 4);
       ptx::mbar_init(empty_bar(s), 1);
     }
     for (int d = 0; d < 2; ++d) {
@@ -1469,30 +1480,13 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     const uint32_t sw = (((piece >> 2) ^ (o0 & 7)) << 4) + (piece & 3) * 4;   // (o0 + 8k) & 7 == o0 & 7
     const uint32_t sw8 = (((piece8 >> 1) ^ (o8 & 7)) << 4) + (piece8 & 1) * 8;  // (o8 + 16k) & 7 == o8 & 7
     const bool base8 = ((reinterpret_cast<uintptr_t>(p.g) & 7) == 0) && ((plane & 3) == 0);
-    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+    for (int unit = p.use_const ? p.num_units : int(blockIdx.x); unit < p.num_units; unit += gridDim.x) {
       int n, u0, u1, p_lo, p_hi;
       unit_rows(unit, n, u0, u1, p_lo, p_hi);
       for (int pr = p_lo; pr <= p_hi; ++pr) {
         ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
         const uint32_t sb = base + st_off + stage * stage_bytes;
         const __nv_bfloat16* grow = p.g + (long long)n * p.cout * plane + (long long)pr * p.wo;
-        if (p.use_const) {
-          // uniform output gradient: the tile is written, not fetched (same swizzled positions, zero beyond Wo)
-#pragma unroll
-          for (int c = 0; c < kChunksPerTile; ++c) {
-            const uint32_t val = (p.wo - c * kChunk - piece * 2) > 0 ? p.const_bits : 0u;
-            uint32_t dst = sb + c * chunk_bytes + o0 * 128 + sw;
-#pragma unroll 8
-            for (int o = o0; o < p.cout; o += 8, dst += 1024)
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(val) : "memory");
-          }
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ready_bar(stage)) : "memory");
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1u;
-          }
-          continue;
-        }
         if (base8 && (((long long)pr * p.wo) & 3) == 0) {
 #pragma unroll
           for (int c = 0; c < kChunksPerTile; ++c) {
@@ -1614,10 +1608,10 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 template <int CIN>
 int launch_bwd_fused(nk_ctx* ctx, const CUtensorMap& tm, const CUtensorMap& tmh, const ConvBP& p, int grid, size_t smem) {
   auto kern = conv_bwd_fused_kernel<CIN>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  // the attribute is per device
+  if (!attr_done[ctx->device & 63]) {
     NK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_done = true;
+    attr_done[ctx->device & 63] = true;
   }
   kern<<<grid, kFThreads, smem, ctx->stream>>>(tm, tmh, p);
   NK_LAUNCHED(ctx, "conv_bwd_fused_tc");
@@ -1629,7 +1623,7 @@ int launch_bwd_fused(nk_ctx* ctx, const CUtensorMap& tm, const CUtensorMap& tmh,
 int nk_conv2d_bwd_fused_tc(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int dw_dtype, void* dbias, float beta_dw,
                            const void* g, const void* x, const void* w, int64_t n, int64_t cin, int64_t h, int64_t wd,
                            int64_t cout, int64_t kh, int64_t kw, const float* g_const) {
-  if (getenv("NK_CONV_DIRECT") || getenv("NK_CONV_UNFUSED_BWD")) return NK_ERR_UNSUPPORTED;
+  if (ctx->conv_engine != NK_CONV_AUTO) return NK_ERR_UNSUPPORTED;
   if (!ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
   if (kh != 3 || kw != 3 || cin < 1 || cin > 3) return NK_ERR_UNSUPPORTED;
   if (cout % 16 != 0 || cout > 128 || wd > 256 || (wd % 8) != 0 || n > 65535) return NK_ERR_UNSUPPORTED;

@@ -178,6 +178,12 @@ int nk_gemm_config(nk_ctx* ctx, int engine) {
   ctx->gemm_engine = engine;
   return NK_OK;
 }
+int nk_conv_config(nk_ctx* ctx, int engine) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  NK_REQUIRE(ctx, engine >= NK_CONV_AUTO && engine <= NK_CONV_UNFUSED, "nk_conv_config: bad engine %d", engine);
+  ctx->conv_engine = engine;
+  return NK_OK;
+}
 const char* nk_last_gemm_kernel(nk_ctx* ctx) { return ctx ? ctx->last_gemm_kernel : "none"; }
 const char* nk_last_conv_kernel(nk_ctx* ctx) { return ctx ? ctx->last_conv_kernel : "none"; }
 

@@ -422,33 +422,56 @@ __global__ void __launch_bounds__(kThreads) nll_bwd_kernel(T* __restrict__ d, co
 }
 
 // ---------------------------------------------------------------- pad
-template <typename T>
+// One thread per E consecutive elements of an output row (E = 2 when the row length is even: one 4- / 8-byte store, a warp
+// writes a contiguous span), index arithmetic in 32 bits whenever the tensor allows it: the first version spent two
+// 64-bit divisions per 2-byte element and ran at 0.6 TB/s (profiles/r02_launches.md).
+template <typename T, int E>
+struct alignas(sizeof(T) * E) PadPack {
+  T v[E];
+};
+
+template <typename T, int E, typename IT>
 __global__ void __launch_bounds__(kThreads) pad2d_fwd_kernel(T* __restrict__ y, const T* __restrict__ x, int64_t planes,
                                                             int64_t h, int64_t w, int64_t ph, int64_t pw, float value) {
-  const int64_t ho = h + 2 * ph, wo = w + 2 * pw;
-  const int64_t total = planes * ho * wo;
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const IT ho = IT(h + 2 * ph), wo = IT(w + 2 * pw), wv = wo / E;
+  const IT total = IT(planes) * ho * wv;
+  const IT stride = IT(gridDim.x) * blockDim.x;
   const T fillv = nk_from_f32<T>(value);
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t q = i % wo, p = (i / wo) % ho, pl = i / (wo * ho);
-    const int64_t sy = p - ph, sx = q - pw;
-    y[i] = (sy >= 0 && sy < h && sx >= 0 && sx < w) ? x[(pl * h + sy) * w + sx] : fillv;  // bit-exact copy
+  for (IT i = IT(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const IT r = i / wv, qv = i - r * wv;     // r = (plane, p)
+    const IT pl = r / ho, p = r - pl * ho;
+    const int sy = int(p) - int(ph);
+    const bool row_in = sy >= 0 && sy < int(h);
+    const T* xr = x + (int64_t(pl) * h + (row_in ? sy : 0)) * w;
+    PadPack<T, E> o;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int sx = int(qv) * E + e - int(pw);
+      o.v[e] = (row_in && sx >= 0 && sx < int(w)) ? xr[sx] : fillv;  // bit-exact copy
+    }
+    reinterpret_cast<PadPack<T, E>*>(y)[i] = o;
   }
 }
 
-template <typename T>
+template <typename T, int E, typename IT>
 __global__ void __launch_bounds__(kThreads) pad2d_bwd_kernel(T* __restrict__ dx, const T* __restrict__ g, int64_t planes,
                                                             int64_t h, int64_t w, int64_t ph, int64_t pw, float beta) {
-  const int64_t ho = h + 2 * ph, wo = w + 2 * pw;
-  const int64_t total = planes * h * w;
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t q = i % w, p = (i / w) % h, pl = i / (w * h);
-    const T gv = g[(pl * ho + p + ph) * wo + q + pw];
-    if (beta != 0.f)
-      dx[i] = nk_from_f32<T>(beta * nk_to_f32<T>(dx[i]) + nk_to_f32<T>(gv));
-    else
-      dx[i] = gv;
+  const IT ho = IT(h + 2 * ph), wo = IT(w + 2 * pw), wv = IT(w) / E, hh = IT(h);
+  const IT total = IT(planes) * hh * wv;
+  const IT stride = IT(gridDim.x) * blockDim.x;
+  for (IT i = IT(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const IT r = i / wv, qv = i - r * wv;     // r = (plane, p)
+    const IT pl = r / hh, p = r - pl * hh;
+    const T* gr = g + (int64_t(pl) * ho + p + ph) * wo + pw + int64_t(qv) * E;
+    PadPack<T, E>* d = reinterpret_cast<PadPack<T, E>*>(dx) + i;
+    PadPack<T, E> o;
+    if (beta != 0.f) o = *d;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const T gv = gr[e];
+      o.v[e] = beta != 0.f ? nk_from_f32<T>(beta * nk_to_f32<T>(o.v[e]) + nk_to_f32<T>(gv)) : gv;
+    }
+    *d = o;
   }
 }
 
@@ -473,6 +496,47 @@ __global__ void __launch_bounds__(kThreads) sgd_kernel(TW* __restrict__ w, TG* _
     }
     if (master) master[i] = wv;
     w[i] = nk_from_f32<TW>(wv);
+  }
+}
+
+// Four elements per thread with 8-/16-byte accesses (the scalar kernel above moved config 4's 16.8 M-element weight at
+// 3.6 TB/s); same arithmetic, element by element, so the results are bit-identical to the scalar kernel.
+template <typename T>
+struct alignas(sizeof(T) * 4) Quad {
+  T v[4];
+};
+template <typename TW, typename TG>
+__global__ void __launch_bounds__(kThreads) sgd_kernel_vec4(TW* __restrict__ w, TG* __restrict__ g, float* __restrict__ buf,
+                                                           float* __restrict__ master, size_t n4, float lr, float l2x2,
+                                                           float mu, float one_minus_damp, int use_momentum, int nesterov,
+                                                           float grad_scale, int write_back_grad) {
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    Quad<TW> wq = reinterpret_cast<Quad<TW>*>(w)[i];
+    Quad<TG> gq = reinterpret_cast<Quad<TG>*>(g)[i];
+    Quad<float> mq, bq;
+    if (master) mq = reinterpret_cast<Quad<float>*>(master)[i];
+    if (use_momentum) bq = reinterpret_cast<Quad<float>*>(buf)[i];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float wv = master ? mq.v[e] : nk_to_f32<TW>(wq.v[e]);
+      float gv = nk_to_f32<TG>(gq.v[e]) * grad_scale;
+      gv += l2x2 * wv;
+      gq.v[e] = nk_from_f32<TG>(gv);
+      if (!use_momentum) {
+        wv -= gv * lr;
+      } else {
+        float b = bq.v[e] * mu + gv * one_minus_damp;
+        bq.v[e] = b;
+        wv -= (nesterov ? (gv + b * mu) : b) * lr;
+      }
+      mq.v[e] = wv;
+      wq.v[e] = nk_from_f32<TW>(wv);
+    }
+    if (write_back_grad) reinterpret_cast<Quad<TG>*>(g)[i] = gq;
+    if (use_momentum) reinterpret_cast<Quad<float>*>(buf)[i] = bq;
+    if (master) reinterpret_cast<Quad<float>*>(master)[i] = mq;
+    reinterpret_cast<Quad<TW>*>(w)[i] = wq;
   }
 }
 
@@ -865,11 +929,18 @@ int nk_pad2d_fwd(nk_ctx* ctx, void* y, const void* x, int64_t planes, int64_t h,
   size_t total = size_t(planes) * size_t(h + 2 * ph) * size_t(w + 2 * pw);
   if (total == 0) return NK_OK;
   NK_REQUIRE(ctx, y && x, "nk_pad2d_fwd: NULL pointer");
-  int blocks = ew_blocks(ctx, total);
+  // E = 2 elements per thread when rows are even (and the base pointer takes the wider store); 32-bit indices when they fit
+  const bool pair = (w + 2 * pw) % 2 == 0 && (reinterpret_cast<uintptr_t>(y) % (2 * nk_dtype_size(dtype))) == 0;
+  const bool small = total < (size_t(1) << 31);
+  int blocks = ew_blocks(ctx, pair ? total / 2 : total);
+#define NK_PAD_F(T, E, IT) pad2d_fwd_kernel<T, E, IT><<<blocks, kThreads, 0, ctx->stream>>>((T*)y, (const T*)x, planes, h, w, ph, pw, value)
+#define NK_PAD_F2(T) (pair ? (small ? NK_PAD_F(T, 2, uint32_t) : NK_PAD_F(T, 2, int64_t)) : (small ? NK_PAD_F(T, 1, uint32_t) : NK_PAD_F(T, 1, int64_t)))
   if (dtype == NK_BF16)
-    pad2d_fwd_kernel<__nv_bfloat16><<<blocks, kThreads, 0, ctx->stream>>>((__nv_bfloat16*)y, (const __nv_bfloat16*)x, planes, h, w, ph, pw, value);
+    NK_PAD_F2(__nv_bfloat16);
   else
-    pad2d_fwd_kernel<float><<<blocks, kThreads, 0, ctx->stream>>>((float*)y, (const float*)x, planes, h, w, ph, pw, value);
+    NK_PAD_F2(float);
+#undef NK_PAD_F2
+#undef NK_PAD_F
   NK_LAUNCHED(ctx, "pad2d_fwd");
   return NK_OK;
 }
@@ -882,11 +953,17 @@ int nk_pad2d_bwd(nk_ctx* ctx, void* dx, const void* g, int64_t planes, int64_t h
   size_t total = size_t(planes) * size_t(h) * size_t(w);
   if (total == 0) return NK_OK;
   NK_REQUIRE(ctx, dx && g, "nk_pad2d_bwd: NULL pointer");
-  int blocks = ew_blocks(ctx, total);
+  const bool pair = w % 2 == 0 && (reinterpret_cast<uintptr_t>(dx) % (2 * nk_dtype_size(dtype))) == 0;
+  const bool small = size_t(planes) * size_t(h + 2 * ph) * size_t(w + 2 * pw) < (size_t(1) << 31);
+  int blocks = ew_blocks(ctx, pair ? total / 2 : total);
+#define NK_PAD_B(T, E, IT) pad2d_bwd_kernel<T, E, IT><<<blocks, kThreads, 0, ctx->stream>>>((T*)dx, (const T*)g, planes, h, w, ph, pw, beta)
+#define NK_PAD_B2(T) (pair ? (small ? NK_PAD_B(T, 2, uint32_t) : NK_PAD_B(T, 2, int64_t)) : (small ? NK_PAD_B(T, 1, uint32_t) : NK_PAD_B(T, 1, int64_t)))
   if (dtype == NK_BF16)
-    pad2d_bwd_kernel<__nv_bfloat16><<<blocks, kThreads, 0, ctx->stream>>>((__nv_bfloat16*)dx, (const __nv_bfloat16*)g, planes, h, w, ph, pw, beta);
+    NK_PAD_B2(__nv_bfloat16);
   else
-    pad2d_bwd_kernel<float><<<blocks, kThreads, 0, ctx->stream>>>((float*)dx, (const float*)g, planes, h, w, ph, pw, beta);
+    NK_PAD_B2(float);
+#undef NK_PAD_B2
+#undef NK_PAD_B
   NK_LAUNCHED(ctx, "pad2d_bwd");
   return NK_OK;
 }
@@ -903,9 +980,23 @@ int nk_sgd_step(nk_ctx* ctx, void* w, int w_dtype, void* g, int g_dtype, float* 
   int blocks = ew_blocks(ctx, n);
   const float l2x2 = 2.f * l2, omd = 1.f - dampening;
   if (l2x2 == 0.f && grad_scale == 1.f) write_back_grad = 0;  // g' == g: storing it back would only move bytes
-#define NK_SGD(TW, TG)                                                                                         \
-  sgd_kernel<TW, TG><<<blocks, kThreads, 0, ctx->stream>>>((TW*)w, (TG*)g, buf, master, n, lr, l2x2, momentum, omd, \
-                                                            use_mom, nesterov, grad_scale, write_back_grad)
+  // body: four elements per thread where every pointer takes the wide access; tail (n % 4 elements): scalar kernel
+  const bool vec = n >= 4 && (reinterpret_cast<uintptr_t>(w) % (4 * nk_dtype_size(w_dtype)) == 0) &&
+                   (reinterpret_cast<uintptr_t>(g) % (4 * nk_dtype_size(g_dtype)) == 0) &&
+                   (!buf || reinterpret_cast<uintptr_t>(buf) % 16 == 0) && (!master || reinterpret_cast<uintptr_t>(master) % 16 == 0);
+  const size_t n4 = vec ? n / 4 : 0, done = n4 * 4, rest = n - done;
+  const int vblocks = ew_blocks(ctx, n4 ? n4 : 1);
+  blocks = ew_blocks(ctx, rest ? rest : 1);
+#define NK_SGD(TW, TG)                                                                                                    \
+  do {                                                                                                                    \
+    if (n4)                                                                                                               \
+      sgd_kernel_vec4<TW, TG><<<vblocks, kThreads, 0, ctx->stream>>>((TW*)w, (TG*)g, buf, master, n4, lr, l2x2, momentum,   \
+                                                                     omd, use_mom, nesterov, grad_scale, write_back_grad); \
+    if (rest)                                                                                                             \
+      sgd_kernel<TW, TG><<<blocks, kThreads, 0, ctx->stream>>>((TW*)w + done, (TG*)g + done, buf ? buf + done : nullptr,    \
+                                                                master ? master + done : nullptr, rest, lr, l2x2, momentum, \
+                                                                omd, use_mom, nesterov, grad_scale, write_back_grad);      \
+  } while (0)
   if (w_dtype == NK_F32 && g_dtype == NK_F32)
     NK_SGD(float, float);
   else if (w_dtype == NK_BF16 && g_dtype == NK_BF16)

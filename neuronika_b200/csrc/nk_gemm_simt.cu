@@ -17,6 +17,8 @@ struct Epilogue {
   const void* bias;
   int bias_bf16;
   int relu;
+  const void* mask = nullptr;   // small-K kernel only: (M, N) tensor of C's type and pitch; v = mask > 0 ? v : 0 before the
+                                // beta accumulate (the ReLU backward of the layer below, relu/mod.rs:71-78)
 };
 
 template <typename TC>
@@ -223,17 +225,17 @@ __device__ __forceinline__ void store4(T* p, bool vec, int valid, const float* v
   }
 }
 
-template <typename TAB, typename TC>
+template <typename TAB, typename TC, int KP>
 __global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
                                                            TC* __restrict__ C, int64_t M, int64_t N, int K,
                                                            int64_t lda, int64_t ldb, int64_t ldc, Epilogue ep) {
   // block: 32 rows x 1024 columns; thread: 4 consecutive columns of all 32 rows, 4 rows in flight at a time so that
   // the (optional) read of C and the stores overlap; every access to C is one 8/16-byte vector
-  __shared__ float As[32][kSkinnyMax];
+  __shared__ float As[32][KP];   // KP = K rounded up to 4: bounds the FMAs (10 -> 12, not 16)
   const int64_t m0 = int64_t(blockIdx.y) * 32;
   const int64_t n = (int64_t(blockIdx.x) * 256 + threadIdx.x) * 4;
-  for (int i = threadIdx.x; i < 32 * kSkinnyMax; i += 256) {
-    const int r = i / kSkinnyMax, k = i - r * kSkinnyMax;
+  for (int i = threadIdx.x; i < 32 * KP; i += 256) {
+    const int r = i / KP, k = i - r * KP;
     As[r][k] = (k < K && m0 + r < M) ? nk_to_f32<TAB>(A[(m0 + r) * lda + k]) : 0.f;
   }
   __syncthreads();
@@ -241,9 +243,10 @@ __global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict
   const int valid = int(N - n < 4 ? N - n : 4);
   const bool vb = valid == 4 && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
   const bool vc = valid == 4 && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-  float b[kSkinnyMax][4];
+  const bool vmask = vc && ((reinterpret_cast<uintptr_t>(ep.mask) & 15) == 0);
+  float b[KP][4];
 #pragma unroll
-  for (int k = 0; k < kSkinnyMax; ++k) {
+  for (int k = 0; k < KP; ++k) {
     if (k < K) load4<TAB>(B + int64_t(k) * ldb + n, vb, valid, b[k]);
     else b[k][0] = b[k][1] = b[k][2] = b[k][3] = 0.f;
   }
@@ -257,18 +260,23 @@ __global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict
   }
   const int rows = int(M - m0 < 32 ? M - m0 : 32);
   for (int r0 = 0; r0 < rows; r0 += 4) {
-    float old[4][4];
+    float old[4][4], msk[4][4];
     if (ep.beta != 0.f) {
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr)
         if (r0 + rr < rows) load4<TC>(C + (m0 + r0 + rr) * ldc + n, vc, valid, old[rr]);
+    }
+    if (ep.mask) {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+        if (r0 + rr < rows) load4<TC>(static_cast<const TC*>(ep.mask) + (m0 + r0 + rr) * ldc + n, vmask, valid, msk[rr]);
     }
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
       if (r0 + rr >= rows) break;
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < kSkinnyMax; ++k) {
+      for (int k = 0; k < KP; ++k) {
         const float a = As[r0 + rr][k];  // zero for k >= K
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, b[k][j], acc[j]);
@@ -276,6 +284,7 @@ __global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float v = ep.alpha * acc[j];
+        if (ep.mask) v = msk[rr][j] > 0.f ? v : 0.f;
         if (ep.beta != 0.f) v += ep.beta * old[rr][j];
         v += bias[j];
         if (ep.relu) v = v > 0.f ? v : 0.f;
@@ -286,45 +295,53 @@ __global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict
   }
 }
 
-template <typename TAB>
-__global__ void __launch_bounds__(128) gemm_small_m_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
+// small-M: block = 8 warps x 128 columns (lane: 4 consecutive) x one slab of k.  Warp w takes the rows k = w, w + 8, ...
+// of the slab with eight 8/16-byte loads of the streamed operand in flight; the M (<= 16) values of A for a row come
+// from shared memory as broadcast 16-byte reads; MP = M rounded up to 4 bounds the FMAs (10 -> 12, not 16).  The eight
+// warps' partial sums meet in shared memory, so a block ends with M x 128 global atomics instead of M x 512 per 128
+// threads: at 10 x 4096 x 8192 the first version (one warp-slab per block) took 94 us, 6x its FMA / HBM floor.
+constexpr int kSmChunk = 256;   // rows of A staged per pass
+template <typename TAB, int MP>
+__global__ void __launch_bounds__(256) gemm_small_m_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
                                                            float* __restrict__ scratch, int M, int64_t N, int64_t K,
                                                            int64_t lda, int64_t ldb, int64_t k_per_block) {
-  // block: 512 columns (thread: 4 consecutive), one slab of k; A rows staged 64 at a time; the streamed operand B is
-  // read with one 8/16-byte load per (k, thread), 8 of them in flight
-  __shared__ __align__(16) float As[64][kSkinnyMax];
-  const int64_t n = (int64_t(blockIdx.x) * 128 + threadIdx.x) * 4;
+  __shared__ __align__(16) float As[kSmChunk][MP];
+  __shared__ float red[MP][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = int64_t(blockIdx.x) * 128 + lane * 4;
   const int64_t k_begin = int64_t(blockIdx.y) * k_per_block;
   int64_t k_end = k_begin + k_per_block;
   if (k_end > K) k_end = K;
   const int valid = n < N ? int(N - n < 4 ? N - n : 4) : 0;
   const bool vb = valid == 4 && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
-  float acc[kSkinnyMax][4];
+  float acc[MP][4];
 #pragma unroll
-  for (int m = 0; m < kSkinnyMax; ++m)
+  for (int m = 0; m < MP; ++m)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
-  for (int64_t k0 = k_begin; k0 < k_end; k0 += 64) {
+  for (int i = threadIdx.x; i < MP * 128; i += 256) (&red[0][0])[i] = 0.f;
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += kSmChunk) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 64 * kSkinnyMax; i += 128) {
-      const int r = i / kSkinnyMax, m = i - r * kSkinnyMax;
-      As[r][m] = (m < M && k0 + r < k_end) ? nk_to_f32<TAB>(A[(k0 + r) * lda + m]) : 0.f;
+    const int rows = int(k_end - k0 < kSmChunk ? k_end - k0 : kSmChunk);
+    for (int i = threadIdx.x; i < kSmChunk * MP; i += 256) {
+      const int r = i / MP, m = i - r * MP;
+      As[r][m] = (m < M && r < rows) ? nk_to_f32<TAB>(A[(k0 + r) * lda + m]) : 0.f;
     }
     __syncthreads();
     if (valid) {
-      const int kk_end = int(k_end - k0 < 64 ? k_end - k0 : 64);
-      for (int kb = 0; kb < kk_end; kb += 8) {
+      for (int kb = warp; kb < rows; kb += 64) {      // 8 rows of this warp per pass: kb, kb + 8, ..., kb + 56
         float bv[8][4];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          if (kb + u < kk_end) load4<TAB>(B + (k0 + kb + u) * ldb + n, vb, valid, bv[u]);
+          if (kb + 8 * u < rows) load4<TAB>(B + (k0 + kb + 8 * u) * ldb + n, vb, valid, bv[u]);
           else bv[u][0] = bv[u][1] = bv[u][2] = bv[u][3] = 0.f;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
+          const int r = kb + 8 * u < rows ? kb + 8 * u : 0;   // (bv is zero beyond the slab)
 #pragma unroll
-          for (int m4 = 0; m4 < kSkinnyMax / 4; ++m4) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[kb + u][m4 * 4]);  // rows >= kk_end are zero
+          for (int m4 = 0; m4 < MP / 4; ++m4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[r][m4 * 4]);
             const float a[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -335,12 +352,16 @@ __global__ void __launch_bounds__(128) gemm_small_m_kernel(const TAB* __restrict
       }
     }
   }
-  if (valid) {
+  __syncthreads();
 #pragma unroll
-    for (int m = 0; m < kSkinnyMax; ++m)
+  for (int m = 0; m < MP; ++m)
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (m < M && j < valid) atomicAdd(&scratch[int64_t(m) * N + n + j], acc[m][j]);
+    for (int j = 0; j < 4; ++j) atomicAdd(&red[m][lane * 4 + j], acc[m][j]);
+  __syncthreads();
+  const int64_t nb = int64_t(blockIdx.x) * 128;
+  for (int i = threadIdx.x; i < M * 128; i += 256) {
+    const int m = i >> 7, c = i & 127;
+    if (nb + c < N) atomicAdd(&scratch[int64_t(m) * N + nb + c], red[m][c]);
   }
 }
 
@@ -351,8 +372,16 @@ int launch_skinny(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int
   if (!transA && !transB && K <= kSkinnyMax && K > 0 && N >= 256) {
     dim3 grid((unsigned)((N + 1023) / 1024), (unsigned)((M + 31) / 32));
     if (grid.y > 65535) return NK_OK;
-    gemm_small_k_kernel<TAB, TC><<<grid, 256, 0, ctx->stream>>>((const TAB*)A, (const TAB*)B, (TC*)C, M, N, (int)K, lda,
-                                                               ldb, ldc, ep);
+#define NK_SK(KP_) gemm_small_k_kernel<TAB, TC, KP_><<<grid, 256, 0, ctx->stream>>>((const TAB*)A, (const TAB*)B, (TC*)C, M, N, (int)K, lda, ldb, ldc, ep)
+    if (K <= 4)
+      NK_SK(4);
+    else if (K <= 8)
+      NK_SK(8);
+    else if (K <= 12)
+      NK_SK(12);
+    else
+      NK_SK(16);
+#undef NK_SK
     NK_LAUNCHED(ctx, "gemm_small_k");
     ctx->last_gemm_kernel = "simt_small_k";
     *handled = true;
@@ -363,17 +392,23 @@ int launch_skinny(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int
     int rc = nk_workspace(ctx, size_t(M) * size_t(N) * sizeof(float), (void**)&scratch);
     if (rc) return rc;
     NK_CUDA(ctx, cudaMemsetAsync(scratch, 0, size_t(M) * size_t(N) * sizeof(float), ctx->stream));
-    const int64_t gx = (N + 511) / 512;
-    // ~8 blocks of 128 threads per SM: the kernel is bound by the latency of the streamed operand, so it wants many
-    // threads with loads in flight (measured at 10 x 4096 x 8192: 1024 blocks 91 us, 256 blocks 150 us; the M*512
-    // atomics each block ends with are not what limits it)
-    int64_t gy = (2 * int64_t(ctx->sm_count) * 4 + gx - 1) / gx;
+    const int64_t gx = (N + 127) / 128;
+    // ~4 blocks of 8 warps per SM, each warp with 8 loads of the streamed operand in flight
+    int64_t gy = (int64_t(ctx->sm_count) * 4 + gx - 1) / gx;
     int64_t k_per_block = (K + gy - 1) / gy;
-    k_per_block = (k_per_block + 63) / 64 * 64;
+    k_per_block = (k_per_block + kSmChunk - 1) / kSmChunk * kSmChunk;
     gy = (K + k_per_block - 1) / k_per_block;
     dim3 grid((unsigned)gx, (unsigned)gy);
-    gemm_small_m_kernel<TAB><<<grid, 128, 0, ctx->stream>>>((const TAB*)A, (const TAB*)B, scratch, (int)M, N, K, lda, ldb,
-                                                           k_per_block);
+#define NK_SM(MP_) gemm_small_m_kernel<TAB, MP_><<<grid, 256, 0, ctx->stream>>>((const TAB*)A, (const TAB*)B, scratch, (int)M, N, K, lda, ldb, k_per_block)
+    if (M <= 4)
+      NK_SM(4);
+    else if (M <= 8)
+      NK_SM(8);
+    else if (M <= 12)
+      NK_SM(12);
+    else
+      NK_SM(16);
+#undef NK_SM
     NK_LAUNCHED(ctx, "gemm_small_m");
     int64_t blocks = (M * N + kThreads - 1) / kThreads;
     splitk_reduce_kernel<TC><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>((TC*)C, scratch, M, N, ldc, 1, ep);
@@ -386,6 +421,26 @@ int launch_skinny(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int
 }
 
 }  // namespace
+
+// C = mask > 0 ? A.B : 0  (+ beta*C) for the skinny NN shape only (K <= 16): the dX product of a 10-wide layer with the ReLU
+// backward of the layer below applied on the way out.  NK_ERR_UNSUPPORTED (nothing done) for every other shape.
+int nk_gemm_simt_small_k_masked(nk_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                                int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype, const void* mask) {
+  if (K > kSkinnyMax || K <= 0 || N < 256 || (M + 31) / 32 > 65535) return NK_ERR_UNSUPPORTED;
+  Epilogue ep{1.f, beta, nullptr, 0, 0, mask};
+  bool handled = false;
+  int rc;
+  if (ab_dtype == NK_F32 && c_dtype == NK_F32)
+    rc = launch_skinny<float, float>(ctx, 0, 0, M, N, K, A, lda, B, ldb, C, ldc, ep, &handled);
+  else if (ab_dtype == NK_BF16 && c_dtype == NK_BF16)
+    rc = launch_skinny<__nv_bfloat16, __nv_bfloat16>(ctx, 0, 0, M, N, K, A, lda, B, ldb, C, ldc, ep, &handled);
+  else if (ab_dtype == NK_BF16 && c_dtype == NK_F32)
+    rc = launch_skinny<__nv_bfloat16, float>(ctx, 0, 0, M, N, K, A, lda, B, ldb, C, ldc, ep, &handled);
+  else
+    rc = launch_skinny<float, __nv_bfloat16>(ctx, 0, 0, M, N, K, A, lda, B, ldb, C, ldc, ep, &handled);
+  if (rc) return rc;
+  return handled ? NK_OK : NK_ERR_UNSUPPORTED;
+}
 
 int nk_gemm_simt(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
                  int64_t lda, const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype,

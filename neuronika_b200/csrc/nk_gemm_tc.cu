@@ -29,6 +29,8 @@ constexpr int kNumThreads = 192;
 constexpr int kRsPitch = 36;                        // floats per staged row (conflict-free 16-byte accesses)
 constexpr uint32_t kRsStageBytes = 4 * 32 * kRsPitch * 4;  // 4 epilogue warps x 32 rows
 constexpr uint32_t kSmemLimit = 232448;  // 227 KB
+constexpr uint32_t kStoreTileBytes = 4096;                       // 32 rows x 128 B (32 f32 or 64 bf16 columns), SWIZZLE_128B
+constexpr uint32_t kEpiStageBytes = 4 * 2 * kStoreTileBytes;     // 4 epilogue warps x 2 buffers = 32 KB (>= kRsStageBytes)
 
 struct GemmParams {
   int64_t M, N, K;
@@ -56,6 +58,10 @@ struct GemmParams {
   // `splits` CTAs per tile, which add their partial sums into C with f32 atomics (C zeroed / scaled by the host).
   int batch, a_batched, b_batched, batch_reduce, splits;
   int64_t c_batch_stride;
+  // epilogue through shared memory + TMA bulk stores (tmap_c): every store instruction of the direct path writes 32
+  // separate 16-byte row pieces; the staged tile leaves as full 128-byte rows.  Set by the host when beta == 0, no mask,
+  // no reduce-scatter, not batched, and C is TMA-addressable.
+  int tma_store;
 };
 
 __device__ __forceinline__ int tile_m_block(const GemmParams& p, int tile) {
@@ -91,33 +97,19 @@ struct Cfg {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
   static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int kStagesMax = (kSmemLimit - 2048) / STAGE_BYTES;
+  // after the ring: 1 KB of barriers, then kEpiStageBytes of epilogue staging (TMA-store tiles / reduce-scatter rows)
+  static constexpr int kStagesMax = (kSmemLimit - 2048 - kEpiStageBytes) / STAGE_BYTES;
   static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
-  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + 2048;  // + alignment slack + barriers
+  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + 2048 + kEpiStageBytes;  // + alignment slack + barriers
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                         : (2 * BLOCK_N <= 256) ? 256 : 512;
 };
 
-template <typename TC>
-__device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int64_t row, int64_t col0, const uint32_t* r,
-                                                       int ncols, bool vec_ok, int64_t c_off = 0, bool atomic = false) {
-  TC* crow = static_cast<TC*>(p.C) + c_off + row * p.ldc + col0;
-  if (atomic) {  // partial sum of a split reduction: f32 atomics (alpha applied, beta handled by the host)
-    if constexpr (sizeof(TC) == 4) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < ncols && col0 + j < p.N) atomicAdd(reinterpret_cast<float*>(crow) + j, p.alpha * __uint_as_float(r[j]));
-    }
-    return;
-  }
-  if (p.rs_world) {
-    const int owner = int(row / p.rs_rows);
-    crow = static_cast<TC*>(p.rs_dst[owner]) + (row - owner * p.rs_rows) * p.ldc + col0;
-  }
-  float v[32];
+// v[j] = alpha * acc[j] + bias (row- or column-indexed) for one 32-column chunk of one output row
+__device__ __forceinline__ void scale_and_bias(const GemmParams& p, int64_t row, int64_t col0, const uint32_t* r, bool full,
+                                               float* v) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = p.alpha * __uint_as_float(r[j]);
-  const bool full = (col0 + 32 <= p.N) && ncols == 32;
   if (p.bias && p.bias_per_row) {
     const float b = p.bias_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[row]) : static_cast<const float*>(p.bias)[row];
 #pragma unroll
@@ -154,6 +146,27 @@ __device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int6
                               : static_cast<const float*>(p.bias)[col0 + j];
     }
   }
+}
+
+template <typename TC>
+__device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int64_t row, int64_t col0, const uint32_t* r,
+                                                       int ncols, bool vec_ok, int64_t c_off = 0, bool atomic = false) {
+  TC* crow = static_cast<TC*>(p.C) + c_off + row * p.ldc + col0;
+  if (atomic) {  // partial sum of a split reduction: f32 atomics (alpha applied, beta handled by the host)
+    if constexpr (sizeof(TC) == 4) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ncols && col0 + j < p.N) atomicAdd(reinterpret_cast<float*>(crow) + j, p.alpha * __uint_as_float(r[j]));
+    }
+    return;
+  }
+  if (p.rs_world) {
+    const int owner = int(row / p.rs_rows);
+    crow = static_cast<TC*>(p.rs_dst[owner]) + (row - owner * p.rs_rows) * p.ldc + col0;
+  }
+  float v[32];
+  const bool full = (col0 + 32 <= p.N) && ncols == 32;
+  scale_and_bias(p, row, col0, r, full, v);
   const TC* mrow = p.mask ? static_cast<const TC*>(p.mask) + row * p.ldc + col0 : nullptr;
   if (full && vec_ok) {
     constexpr int V = 16 / sizeof(TC);
@@ -203,7 +216,7 @@ __device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int6
 template <int BLOCK_N, bool A_MN, bool B_MN, typename TC, bool BATCH = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   using C_ = Cfg<BLOCK_N>;
   constexpr int kStages = C_::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -226,6 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_b);
+    if (p.tma_store) ptx::prefetch_tmap(&tmap_c);
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(full_bar(s), 1);
       ptx::mbar_init(empty_bar(s), 1);
@@ -354,8 +368,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int q = warp_idx & 3;  // TMEM lane quarter this warp may access
     const bool vec_ok = ((p.ldc * int64_t(sizeof(TC))) % 16 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
-    float* rs_stage = reinterpret_cast<float*>(smem_raw + (bar_base + 512 - ptx::smem_u32(smem_raw)));
+    const uint32_t epi_stage = bar_base + 1024;   // 1024-byte aligned (SWIZZLE_128B store tiles)
+    float* rs_stage = reinterpret_cast<float*>(smem_raw + (epi_stage - ptx::smem_u32(smem_raw)));
     (void)rs_stage;
+    uint32_t store_buf = 0;                      // which of this warp's two store tiles the next chunk uses
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -367,6 +383,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::mbar_wait(tmem_full_bar(as), aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BLOCK_N);
+      if constexpr (BLOCK_N >= 64 && !BATCH) {
+        if (p.tma_store) {
+          // ---- staged epilogue: 32 rows x 128 bytes per tile (32 f32 / 64 bf16 columns), written 128B-swizzled so that
+          // the eight lanes of a store phase hit distinct banks, then ONE bulk tensor store per tile (TMA clips M/N tails)
+          constexpr int kColsPerTile = 128 / int(sizeof(TC));
+          const int64_t row0 = int64_t(m_blk) * BLOCK_M + q * 32;
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_N / kColsPerTile; ++c) {
+            const int64_t col0 = int64_t(n_blk) * BLOCK_N + c * kColsPerTile;
+            if (col0 >= p.N) break;
+            const uint32_t tile = epi_stage + (uint32_t(warp_idx - 2) * 2u + store_buf) * kStoreTileBytes;
+            if (lane == 0) ptx::tma_store_wait_read<1>();   // the store that last read this buffer has finished reading
+            __syncwarp();
+            const uint32_t rowaddr = tile + uint32_t(lane) * 128u;
+            const uint32_t sx = uint32_t(lane & 7);
+            if constexpr (sizeof(TC) == 4) {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+              ptx::tmem_ld_wait();
+              float v[32];
+              scale_and_bias(p, row, col0, r, col0 + 32 <= p.N, v);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (p.relu) o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((uint32_t(j) ^ sx) << 4)), "f"(o.x),
+                             "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+              }
+            } else {
+#pragma unroll
+              for (int hc = 0; hc < 2; ++hc) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(taddr + c * 64 + hc * 32, r);
+                ptx::tmem_ld_wait();
+                float v[32];
+                scale_and_bias(p, row, col0 + hc * 32, r, col0 + hc * 32 + 32 <= p.N, v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint32_t w[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float a = v[8 * j + 2 * e], b = v[8 * j + 2 * e + 1];
+                    if (p.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
+                    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                    w[e] = *reinterpret_cast<uint32_t*>(&h);
+                  }
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((uint32_t(hc * 4 + j) ^ sx) << 4)),
+                               "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                }
+              }
+            }
+            ptx::fence_proxy_async();   // generic-proxy writes -> visible to the bulk-copy (async proxy) read
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&tmap_c, tile, int32_t(col0), int32_t(row0));
+              ptx::tma_store_commit();
+            }
+            store_buf ^= 1u;
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));
+          as ^= 1;
+          if (as == 0) aphase ^= 1u;
+          continue;
+        }
+      }
       if (BLOCK_N >= 32) {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -418,6 +501,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
+    if (p.tma_store && lane == 0) ptx::tma_store_wait<0>();   // shared memory must outlive the bulk stores that read it
   }
 
   ptx::tc_fence_before();
@@ -450,19 +534,34 @@ int make_tmap_2d(nk_ctx* ctx, CUtensorMap* tm, const void* base, int64_t rows, i
   return NK_OK;
 }
 
+// output tensor map of the staged epilogue: (M, N) row-major with leading dimension ldc, boxes of 32 rows x 128 bytes
+int make_tmap_c(nk_ctx* ctx, CUtensorMap* tm, void* base, int64_t rows, int64_t cols, int64_t ld, int c_dtype) {
+  if (!ctx->encode_tiled) return NK_ERR_UNSUPPORTED;
+  const size_t es = nk_dtype_size(c_dtype);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / es), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      tm, c_dtype == NK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box,
+      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? NK_OK : NK_ERR_UNSUPPORTED;
+}
+
 uint32_t env_u32(const char* name, uint32_t dflt) {
   const char* v = getenv(name);
   return v ? (uint32_t)strtoul(v, nullptr, 0) : dflt;
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, typename TC, bool BATCH = false>
-int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p) {
+int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p, const CUtensorMap* tc = nullptr) {
   using C_ = Cfg<BLOCK_N>;
   auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, TC, BATCH>;
   static bool attr_done[64] = {};  // per template instantiation and device (the attribute is per device)
   if (!attr_done[ctx->device & 63]) {
-    const uint32_t max_smem = C_::SMEM_BYTES + kRsStageBytes <= kSmemLimit ? C_::SMEM_BYTES + kRsStageBytes : C_::SMEM_BYTES;
-    NK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+    static_assert(C_::SMEM_BYTES <= kSmemLimit && kRsStageBytes <= kEpiStageBytes, "shared memory budget");
+    NK_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM_BYTES));
     attr_done[ctx->device & 63] = true;
   }
   p.num_n_blocks = int((p.N + BLOCK_N - 1) / BLOCK_N);
@@ -487,9 +586,9 @@ int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
   if (p.rs_world) {
     if (BLOCK_N != 256 || sizeof(TC) != 4 || p.N % 4 != 0)
       return nk_set_error(ctx, NK_ERR_UNSUPPORTED, "tcgen05 gemm: reduce-scatter epilogue needs 128x256 tiles, f32, N %% 4 == 0");
-    smem += kRsStageBytes;
   }
-  kern<<<grid, kNumThreads, smem, ctx->stream>>>(ta, tb, p);
+  if (!tc || BLOCK_N < 64 || BATCH) p.tma_store = 0;
+  kern<<<grid, kNumThreads, smem, ctx->stream>>>(ta, tb, p.tma_store ? *tc : ta, p);
   ctx->launches++;
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess)
@@ -500,11 +599,11 @@ int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
 }
 
 template <bool A_MN, bool B_MN, typename TC>
-int launch_bn(nk_ctx* ctx, int block_n, const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p) {
+int launch_bn(nk_ctx* ctx, int block_n, const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p, const CUtensorMap* tc) {
   switch (block_n) {
-    case 256: return launch_cfg<256, A_MN, B_MN, TC>(ctx, ta, tb, p);
-    case 128: return launch_cfg<128, A_MN, B_MN, TC>(ctx, ta, tb, p);
-    case 64: return launch_cfg<64, A_MN, B_MN, TC>(ctx, ta, tb, p);
+    case 256: return launch_cfg<256, A_MN, B_MN, TC>(ctx, ta, tb, p, tc);
+    case 128: return launch_cfg<128, A_MN, B_MN, TC>(ctx, ta, tb, p, tc);
+    case 64: return launch_cfg<64, A_MN, B_MN, TC>(ctx, ta, tb, p, tc);
     default:
       if (!B_MN) {
         if (block_n == 32) return launch_cfg<32, A_MN, false, TC>(ctx, ta, tb, p);
@@ -549,7 +648,15 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
     // (profiles/r01_gemm_tile_sweep.md), so the wide tile wins even when it quantises worse over 148 SMs.
     block_n = 256;
   }
-  block_n = (int)env_u32("NK_GEMM_BLOCK_N", (uint32_t)block_n);
+  // development knobs (tile sweeps, descriptor sweeps on hardware): the environment is read ONCE per process
+  struct Knobs {
+    uint32_t block_n, a_lbo, a_sbo, b_lbo, b_sbo, direct_store;
+    Knobs() : block_n(env_u32("NK_GEMM_BLOCK_N", 0)), a_lbo(env_u32("NK_DESC_A_LBO", 0)), a_sbo(env_u32("NK_DESC_A_SBO", 0)),
+              b_lbo(env_u32("NK_DESC_B_LBO", 0)), b_sbo(env_u32("NK_DESC_B_SBO", 0)),
+              direct_store(env_u32("NK_GEMM_DIRECT_STORE", 0)) {}
+  };
+  static const Knobs knobs;
+  if (knobs.block_n) block_n = int(knobs.block_n);
 
   GemmParams p;
   p.M = M;
@@ -589,11 +696,10 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   p.b_lbo = b_mn ? BLOCK_K * 128 : 16;
   p.b_sbo = 1024;
   p.b_kstep = b_mn ? UMMA_K * 128 : UMMA_K * 2;
-  // debugging overrides (descriptor sweeps on hardware)
-  p.a_lbo = env_u32("NK_DESC_A_LBO", p.a_lbo);
-  p.a_sbo = env_u32("NK_DESC_A_SBO", p.a_sbo);
-  p.b_lbo = env_u32("NK_DESC_B_LBO", p.b_lbo);
-  p.b_sbo = env_u32("NK_DESC_B_SBO", p.b_sbo);
+  if (knobs.a_lbo) p.a_lbo = knobs.a_lbo;
+  if (knobs.a_sbo) p.a_sbo = knobs.a_sbo;
+  if (knobs.b_lbo) p.b_lbo = knobs.b_lbo;
+  if (knobs.b_sbo) p.b_sbo = knobs.b_sbo;
 
   CUtensorMap ta, tb;
   int rc;
@@ -616,9 +722,16 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   const int bi = block_n == 256 ? 0 : block_n == 128 ? 1 : block_n == 64 ? 2 : block_n == 32 ? 3 : 4;
   ctx->last_gemm_kernel = names[a_mn][b_mn][bi];
 
-#define NK_TC(AM, BM_)                                                            \
-  (c_dtype == NK_BF16 ? launch_bn<AM, BM_, __nv_bfloat16>(ctx, block_n, ta, tb, p) \
-                      : launch_bn<AM, BM_, float>(ctx, block_n, ta, tb, p))
+  // staged TMA-store epilogue wherever the output is plain (no accumulate, mask or reduce-scatter) and TMA-addressable
+  CUtensorMap tc;
+  p.tma_store = 0;
+  if (beta == 0.f && !mask && p.rs_world == 0 && block_n >= 64 && knobs.direct_store == 0 &&
+      (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * int64_t(nk_dtype_size(c_dtype))) % 16 == 0) {
+    if (make_tmap_c(ctx, &tc, C, M, N, ldc, c_dtype) == NK_OK) p.tma_store = 1;
+  }
+#define NK_TC(AM, BM_)                                                                 \
+  (c_dtype == NK_BF16 ? launch_bn<AM, BM_, __nv_bfloat16>(ctx, block_n, ta, tb, p, &tc) \
+                      : launch_bn<AM, BM_, float>(ctx, block_n, ta, tb, p, &tc))
   if (!a_mn && !b_mn) return NK_TC(false, false);
   if (!a_mn && b_mn) return NK_TC(false, true);
   if (a_mn && !b_mn) return NK_TC(true, false);
@@ -666,6 +779,7 @@ int nk_gemm_tcgen05_batched(nk_ctx* ctx, int transA, int transB, int64_t M, int6
   p.num_k_blocks = int((K + BLOCK_K - 1) / BLOCK_K);
   p.rs_world = 0, p.m_rot = 0, p.rs_rows = M;
   for (int i = 0; i < 8; ++i) p.rs_dst[i] = nullptr;
+  p.tma_store = 0;
   p.batch = int(batch), p.a_batched = strideA != 0, p.b_batched = strideB != 0, p.batch_reduce = reduce ? 1 : 0, p.splits = 1;
   p.c_batch_stride = strideC;
   p.a_lbo = a_mn ? BLOCK_K * 128 : 16, p.a_sbo = 1024, p.a_kstep = a_mn ? UMMA_K * 128 : UMMA_K * 2;
@@ -739,6 +853,11 @@ int nk_gemm_relu_bwd(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, 
   if (ab_dtype == NK_BF16 && ctx->gemm_engine != NK_GEMM_SIMT) {
     int rc = nk_gemm_tcgen05(ctx, transA, transB, M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, c_dtype, nullptr, NK_F32, 0,
                              relu_operand);
+    if (rc != NK_ERR_UNSUPPORTED) return rc;
+  }
+  // the skinny NN shape (K <= 16: the layer above is 10 wide) masks in its own epilogue
+  if (!transA && !transB) {
+    int rc = nk_gemm_simt_small_k_masked(ctx, M, N, K, A, lda, B, ldb, beta, C, ldc, ab_dtype, c_dtype, relu_operand);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }
   // operands the tensor-core engine cannot take: the product into a temporary, then the ordinary ReLU backward

@@ -585,13 +585,18 @@ struct Convolution : Forward {  // convolution/mod.rs:296-355
   ConvArgs a;
   const char* name() const override { return "Convolution"; }
   void forward() override { run(nullptr, nullptr); }
-  void run(Tensor* bias, Tensor* out) {
+  void run(Tensor* bias, Tensor* out, int relu = 0) {
     Tensor* o = out ? out : data.get();
-    ck(ctx, nk_conv2d_fwd(ctx, o->wptr(), input->rptr(), kernel->rptr(), bias ? bias->rptr() : nullptr, 0, a.n, a.cin,
+    ck(ctx, nk_conv2d_fwd(ctx, o->wptr(), input->rptr(), kernel->rptr(), bias ? bias->rptr() : nullptr, relu, a.n, a.cin,
                           a.h, a.w, a.cout, a.kh, a.kw, a.sh, a.sw, a.dh, a.dw, a.groups, o->dtype));
   }
 };
-void Addition::run_fused_conv() { fused_conv->run(right.get(), data.get()); }
+void Addition::run_fused_conv() {
+  if (fused_relu_out)
+    fused_conv->run(right.get(), fused_relu_out.get(), 1);  // y = relu(conv + b) in the convolution's epilogue
+  else
+    fused_conv->run(right.get(), data.get());
+}
 struct ConvolutionBackward : Backward {  // convolution/mod.rs:357-510: input first, then kernel (:380-388)
   nk_ctx* ctx;
   TensorP input, kernel;
@@ -1055,6 +1060,30 @@ void fuse(nkg_var* v) {
     if (add->left.use_count() != 2) continue;
     add->fused_conv = it->second;
     it->second->skip = true;
+  }
+  // ... followed by ReLU: relu(conv + bias) in the convolution's epilogue, exactly as for the Linear layer above (the
+  // ReLU backward masks with y > 0, identical to z > 0)
+  {
+    std::map<Tensor*, std::shared_ptr<Addition>> fused_adds;
+    for (auto& kv : v->fwd)
+      if (auto add = std::dynamic_pointer_cast<Addition>(kv.second))
+        if (add->fused_conv && !add->fused_relu_out) fused_adds[add->data.get()] = add;
+    for (auto& kv : v->fwd) {
+      auto relu = std::dynamic_pointer_cast<ReLU>(kv.second);
+      if (!relu || relu->skip || fused_adds.empty()) continue;
+      auto it = fused_adds.find(relu->operand.get());
+      if (it == fused_adds.end()) continue;
+      auto add = it->second;
+      std::shared_ptr<ReLUBackward> rb;
+      for (auto& kb : v->bwd)
+        if (auto c = std::dynamic_pointer_cast<ReLUBackward>(kb.second))
+          if (c->operand_data.get() == add->data.get()) rb = c;
+      if (add->data.use_count() != (rb ? 3 : 2)) continue;
+      if (relu->data->dtype != add->data->dtype) continue;
+      add->fused_relu_out = relu->data;
+      relu->skip = true;
+      if (rb) rb->operand_data = relu->data;
+    }
   }
   // level 2: ReLU backward into the epilogue of the matmul that produces its output gradient
   if (g_fusion >= 2) {

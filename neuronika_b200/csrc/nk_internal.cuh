@@ -34,6 +34,7 @@ struct nk_ctx {
   size_t workspace_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int gemm_engine = NK_GEMM_AUTO;
+  int conv_engine = NK_CONV_AUTO;
   const char* last_gemm_kernel = "none";
   const char* last_conv_kernel = "none";
   void* encode_tiled = nullptr;  // cuTensorMapEncodeTiled, fetched through the runtime
@@ -133,6 +134,8 @@ __device__ __forceinline__ float nk_warp_max(float v) {
   } while (0)
 
 // engines implemented in other translation units
+int nk_gemm_simt_small_k_masked(nk_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                                int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype, const void* mask);
 int nk_gemm_simt(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha,
                  const void* A, int64_t lda, const void* B, int64_t ldb, float beta, void* C,
                  int64_t ldc, int ab_dtype, int c_dtype, const void* bias, int bias_dtype, int relu);

@@ -59,6 +59,11 @@ class Device:
     def gemm_engine(self, engine: str) -> None:
         L.check(L.lib.nk_gemm_config(self.ctx, {"auto": 0, "simt": 1, "tcgen05": 2}[engine]), self.ctx)
 
+    def conv_engine(self, engine: str) -> None:
+        """"auto": tensor-core kernels wherever they apply; "direct": CUDA-core kernels only; "unfused": auto without the
+        one-pass dX + dW backward kernel"""
+        L.check(L.lib.nk_conv_config(self.ctx, {"auto": 0, "direct": 1, "unfused": 2}[engine]), self.ctx)
+
     @property
     def last_gemm_kernel(self) -> str:
         return L.lib.nk_last_gemm_kernel(self.ctx).decode()

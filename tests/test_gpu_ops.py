@@ -505,13 +505,12 @@ def test_conv2d_tensor_core_forward(nk, dev, O, shape, cout, k):
     wb = np.maximum(want + b[None, :, None, None], 0)
     assert np.all(np.abs(yb.as_ndarray() - wb) <= 2e-3 * scale + 2.0 ** -8 * np.abs(wb))
     # the direct engine gives the same numbers up to bf16 rounding of the output
-    import os
-    os.environ["NK_CONV_DIRECT"] = "1"
+    dev.conv_engine("direct")
     try:
         yd = ops.conv2d(dx_, dw_)
         assert dev.last_conv_kernel == "direct_fwd"
     finally:
-        del os.environ["NK_CONV_DIRECT"]
+        dev.conv_engine("auto")
     assert np.all(np.abs(yd.as_ndarray() - y.as_ndarray()) <= 2e-3 * scale + 2.0 ** -7 * np.abs(want))
 
 
@@ -608,13 +607,13 @@ def test_conv2d_tensor_core_backward_fused(nk, dev, O, shape, cout):
     assert np.all(np.abs(dx2.as_ndarray() - want_dx) <= 2e-3 * sx + 2.0 ** -8 * np.abs(want_dx))
     assert np.all(np.abs(dw2.as_ndarray() - want_dw) <= 2e-3 * sw + 1e-5)
 
-    os.environ["NK_CONV_UNFUSED_BWD"] = "1"    # the two separate tensor-core kernels: same dx bits, same dW to f32 noise
+    dev.conv_engine("unfused")                 # the two separate tensor-core kernels: same dx bits, same dW to f32 noise
     try:
         dx3, dw3 = dev.from_ndarray(d0, nk.BF16), dev.from_ndarray(w0, nk.F32)
         ops.conv2d_bwd(dx3, dw3, G, X, Wd, beta_dx=0.0, beta_dw=0.0)
         assert dev.last_conv_kernel == "tcgen05_implicit_gemm_dx"
     finally:
-        del os.environ["NK_CONV_UNFUSED_BWD"]
+        dev.conv_engine("auto")
     assert np.array_equal(dx3.as_ndarray(), dx2.as_ndarray())
     assert np.all(np.abs(dw3.as_ndarray() - dw2.as_ndarray()) <= 1e-4 * sw + 1e-6)
 
