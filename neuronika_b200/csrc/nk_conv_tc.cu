@@ -1209,6 +1209,8 @@ struct ConvBP {
   __nv_bfloat16* dx;
   float beta_dx;
   float* scratch;
+  int dbg;              // development only (NK_CONV_DBG bit mask, read once): 1 no dW UMMAs, 2 no dX UMMAs, 4 no col2im,
+                        // 8 no tap shifting, 16 no x TMA -- wrong results, used to time the parts of the pipeline
   int use_const;        // the output gradient is one value everywhere (backward(seed) on the convolution's own output):
   uint32_t const_bits;  // the loaders synthesise the G tiles (value packed twice as bf16) instead of reading 2|G| bytes
 };
@@ -1333,7 +1335,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             const uint32_t tmem_d = tmem_base + uint32_t(db * kFDxCols + hf * 32);
-            for (int ks = 0; ks < p.cout / 16; ++ks) {
+            for (int ks = 0; ks < ((p.dbg & 2) ? 0 : p.cout / 16); ++ks) {
               const uint64_t adesc = ptx::make_smem_desc_sw128(sb + 2 * hf * chunk_bytes + ks * 2048, chunk_bytes, 1024);
               const uint64_t bdesc = ptx::make_smem_desc_sw128(base + (ks >> 2) * 4096 + (ks & 3) * 32, 16, 1024);
               ptx::mma_f16_ss(tmem_d, adesc, bdesc, idesc_dx, ks != 0 ? 1u : 0u);
@@ -1342,7 +1344,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           ptx::mma_commit(d_full_bar(db));
           db ^= 1;
           if (db == 0) dphase ^= 1u;
-          if (pr >= u0) {
+          if (pr >= u0 && !(p.dbg & 1)) {
             for (int c = 0; c < p.cpr; ++c) {
               const uint64_t adesc = ptx::make_smem_desc_sw128(sb + c * chunk_bytes, 16, 1024);
               const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + c * chunk_bytes + g_bytes, 16, 1024);
@@ -1374,7 +1376,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         unit_rows(unit, n, u0, u1, p_lo, p_hi);
         for (int pr = p_lo; pr <= p_hi; ++pr) {
           ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
-          if (pr >= u0) {
+          if (pr >= u0 && !(p.dbg & 16)) {
             ptx::mbar_expect_tx(fullx_bar(stage), tx);
             for (int c = 0; c < p.cpr; ++c) {
               const uint32_t sc = base + st_off + stage * stage_bytes + c * chunk_bytes + g_bytes;
@@ -1407,7 +1409,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       unit_rows(unit, n, u0, u1, p_lo, p_hi);
       for (int pr = p_lo; pr <= p_hi; ++pr) {
         ptx::mbar_wait_relaxed(fullx_bar(stage), phase);
-        if (pr >= u0) {
+        if (pr >= u0 && !(p.dbg & 8)) {
           any_owned = true;  // at least one dW chain ran: every accumulator has been written (>= 4 UMMAs >= nacc)
           uint8_t* sp = base_ptr + st_off + stage * stage_bytes;
           for (int c = 0; c < p.cpr; ++c) {
@@ -1567,6 +1569,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         if (lane == 0) ptx::mbar_arrive(d_empty_bar(db));
         db ^= 1;
         if (db == 0) dphase ^= 1u;
+        if (p.dbg & 4) continue;
         // publish the two last pixels of this warp for the next warp's lanes 0 and 1
         float* mine = Hx + (parity * 8 + pw) * 64;
         if (lane >= 30) {
@@ -1641,6 +1644,8 @@ int nk_conv2d_bwd_fused_tc(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int 
   p.fuse_dbias = (dbias != nullptr && p.R < 16) ? 1 : 0;
   p.use_const = g_const != nullptr;
   p.const_bits = 0;
+  static const int dbg_mask = getenv("NK_CONV_DBG") ? atoi(getenv("NK_CONV_DBG")) : 0;
+  p.dbg = dbg_mask;
   if (g_const) {
     if (dbias && !p.fuse_dbias) return NK_ERR_UNSUPPORTED;   // the separate bias-gradient pass reads G from memory
     const __nv_bfloat16 hv = __float2bfloat16_rn(*g_const);

@@ -62,6 +62,7 @@ struct GemmParams {
   // separate 16-byte row pieces; the staged tile leaves as full 128-byte rows.  Set by the host when beta == 0, no mask,
   // no reduce-scatter, not batched, and C is TMA-addressable.
   int tma_store;
+  int cta_pairs;   // host-side: launch the cta_group::2 variant (the B tensor map then has 128-row boxes)
 };
 
 __device__ __forceinline__ int tile_m_block(const GemmParams& p, int tile) {
@@ -92,10 +93,10 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
   n_blk = in_group / gm;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG = 1>
 struct Cfg {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-  static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;   // a CTA of a pair stages half of the B tile
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   // after the ring: 1 KB of barriers, then kEpiStageBytes of epilogue staging (TMA-store tiles / reduce-scatter rows)
   static constexpr int kStagesMax = (kSmemLimit - 2048 - kEpiStageBytes) / STAGE_BYTES;
@@ -213,12 +214,19 @@ __device__ __forceinline__ void epilogue_store_chunk32(const GemmParams& p, int6
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, typename TC, bool BATCH = false>
+// CG = 2: CTA pairs (cta_group::2).  A cluster of two CTAs owns a 256 x BLOCK_N tile: CTA r loads rows [128r, 128r + 128) of
+// the A tile and rows [BLOCK_N/2 r, ...) of the B tile into its own shared memory (32 KB per stage instead of 48 KB: six
+// stages in flight instead of four, and a third less L2 -> SM traffic per flop), the even CTA issues one M = 256 UMMA per
+// k step for both, and each CTA drains its own 128 accumulator rows from its own TMEM.
+template <int BLOCK_N, bool A_MN, bool B_MN, typename TC, bool BATCH = false, int CG = 1>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
-  using C_ = Cfg<BLOCK_N>;
+  using C_ = Cfg<BLOCK_N, CG>;
   constexpr int kStages = C_::kStages;
+  constexpr int LOAD_N = BLOCK_N / CG;
+  static_assert(CG == 1 || (CG == 2 && !BATCH && BLOCK_N == 256), "CTA pairs: plain 256-wide tiles only");
+  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms: 1024 B aligned
   const uint32_t smem_a0 = smem_base;
@@ -246,16 +254,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tmem_full_bar(s), 1);
-      ptx::mbar_init(tmem_empty_bar(s), 4);  // one arrive per epilogue warp
+      ptx::mbar_init(tmem_empty_bar(s), 4 * CG);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     ptx::fence_barrier_init();
   }
   if (warp_idx == 1) {
-    ptx::tmem_alloc(tmem_slot, C_::TMEM_COLS);
-    ptx::tmem_relinquish();
+    if constexpr (CG == 2) {
+      ptx::tmem_alloc_2sm(tmem_slot, C_::TMEM_COLS);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(tmem_slot, C_::TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2)
+    ptx::cluster_sync();   // the peer's barriers are initialised before anything signals them
+  else
+    __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -277,15 +293,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = int(blockIdx.x) / CG; tile < num_tiles; tile += int(gridDim.x) / CG) {
         int m_blk, n_blk, b0 = 0, b1 = 1;
         tile_coords(p, BATCH ? tile % tiles_mn : tile, m_blk, n_blk);
         if (BATCH) batch_range(tile / tiles_mn, b0, b1);
-        const int m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        const int m0 = (m_blk * CG + int(cta_rank)) * BLOCK_M, n0 = n_blk * BLOCK_N + int(cta_rank) * LOAD_N;
         for (int bb = b0; bb < b1; ++bb)
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          ptx::mbar_expect_tx(full_bar(stage), C_::STAGE_BYTES);
+          if constexpr (CG == 2) {
+            // both CTAs' loads complete on the leader's barrier, which expects the bytes of both
+            if (cta_rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * C_::STAGE_BYTES);
+          } else {
+            ptx::mbar_expect_tx(full_bar(stage), C_::STAGE_BYTES);
+          }
           const int k0 = kb * BLOCK_K;
           const uint32_t sa = smem_a0 + stage * C_::A_BYTES;
           const uint32_t sb = smem_b0 + stage * C_::B_BYTES;
@@ -294,26 +315,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int c = 0; c < BLOCK_M / 64; ++c) {
               if (BATCH && p.a_batched)
                 ptx::tma_load_3d(sa + c * (64 * BLOCK_K * 2), &tmap_a, full_bar(stage), m0 + c * 64, k0, bb);
+              else if (CG == 2)
+                ptx::tma_load_2d_2sm(sa + c * (64 * BLOCK_K * 2), &tmap_a, full_bar(stage), m0 + c * 64, k0);
               else
                 ptx::tma_load_2d(sa + c * (64 * BLOCK_K * 2), &tmap_a, full_bar(stage), m0 + c * 64, k0);
             }
           } else {  // stored (M, K): one box of 64 (k) x 128 (m)
             if (BATCH && p.a_batched)
               ptx::tma_load_3d(sa, &tmap_a, full_bar(stage), k0, m0, bb);
+            else if (CG == 2)
+              ptx::tma_load_2d_2sm(sa, &tmap_a, full_bar(stage), k0, m0);
             else
               ptx::tma_load_2d(sa, &tmap_a, full_bar(stage), k0, m0);
           }
           if (B_MN) {  // stored (K, N)
 #pragma unroll
-            for (int c = 0; c < BLOCK_N / 64; ++c) {
+            for (int c = 0; c < LOAD_N / 64; ++c) {
               if (BATCH && p.b_batched)
                 ptx::tma_load_3d(sb + c * (64 * BLOCK_K * 2), &tmap_b, full_bar(stage), n0 + c * 64, k0, bb);
+              else if (CG == 2)
+                ptx::tma_load_2d_2sm(sb + c * (64 * BLOCK_K * 2), &tmap_b, full_bar(stage), n0 + c * 64, k0);
               else
                 ptx::tma_load_2d(sb + c * (64 * BLOCK_K * 2), &tmap_b, full_bar(stage), n0 + c * 64, k0);
             }
           } else {  // stored (N, K)
             if (BATCH && p.b_batched)
               ptx::tma_load_3d(sb, &tmap_b, full_bar(stage), k0, n0, bb);
+            else if (CG == 2)
+              ptx::tma_load_2d_2sm(sb, &tmap_b, full_bar(stage), k0, n0);
             else
               ptx::tma_load_2d(sb, &tmap_b, full_bar(stage), k0, n0);
           }
@@ -325,14 +354,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp_idx == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    // ===================================================== MMA issuer (CTA pairs: the even CTA issues for both)
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * CG, BLOCK_N, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = int(blockIdx.x) / CG; tile < num_tiles; tile += int(gridDim.x) / CG) {
         ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(as * BLOCK_N);
@@ -349,16 +378,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t bdesc = ptx::make_smem_desc_sw128(smem_b0 + stage * C_::B_BYTES, p.b_lbo, p.b_sbo);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            ptx::mma_f16_ss(tmem_d, adesc + uint64_t((k * p.a_kstep) >> 4), bdesc + uint64_t((k * p.b_kstep) >> 4),
-                            idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2)
+              ptx::mma_f16_ss_2sm(tmem_d, adesc + uint64_t((k * p.a_kstep) >> 4), bdesc + uint64_t((k * p.b_kstep) >> 4),
+                                  idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              ptx::mma_f16_ss(tmem_d, adesc + uint64_t((k * p.a_kstep) >> 4), bdesc + uint64_t((k * p.b_kstep) >> 4),
+                              idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          ptx::mma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if constexpr (CG == 2)
+            ptx::mma_commit_2sm(empty_bar(stage));  // the slot of BOTH CTAs is reusable once these MMAs retire
+          else
+            ptx::mma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        ptx::mma_commit(tmem_full_bar(as));  // accumulator complete -> epilogue
+        if constexpr (CG == 2)
+          ptx::mma_commit_2sm(tmem_full_bar(as));  // accumulator complete -> the epilogue warps of both CTAs
+        else
+          ptx::mma_commit(tmem_full_bar(as));  // accumulator complete -> epilogue
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
@@ -374,12 +413,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t store_buf = 0;                      // which of this warp's two store tiles the next chunk uses
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = int(blockIdx.x) / CG; tile < num_tiles; tile += int(gridDim.x) / CG) {
       int m_blk, n_blk;
       tile_coords(p, BATCH ? tile % tiles_mn : tile, m_blk, n_blk);
       const int64_t c_off = (BATCH && !p.batch_reduce) ? int64_t(tile / tiles_mn) * p.c_batch_stride : 0;
       const bool atomic = BATCH && p.batch_reduce;
-      const int64_t row = int64_t(m_blk) * BLOCK_M + q * 32 + lane;
+      const int64_t tile_row0 = (int64_t(m_blk) * CG + cta_rank) * BLOCK_M;   // first output row of this CTA's half
+      const int64_t row = tile_row0 + q * 32 + lane;
       ptx::mbar_wait(tmem_full_bar(as), aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BLOCK_N);
@@ -388,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           // ---- staged epilogue: 32 rows x 128 bytes per tile (32 f32 / 64 bf16 columns), written 128B-swizzled so that
           // the eight lanes of a store phase hit distinct banks, then ONE bulk tensor store per tile (TMA clips M/N tails)
           constexpr int kColsPerTile = 128 / int(sizeof(TC));
-          const int64_t row0 = int64_t(m_blk) * BLOCK_M + q * 32;
+          const int64_t row0 = tile_row0 + q * 32;
 #pragma unroll 1
           for (int c = 0; c < BLOCK_N / kColsPerTile; ++c) {
             const int64_t col0 = int64_t(n_blk) * BLOCK_N + c * kColsPerTile;
@@ -444,7 +484,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));
+          if (lane == 0) {
+            if constexpr (CG == 2)
+              ptx::mbar_arrive_leader(tmem_empty_bar(as));   // the MMA issuer lives in the even CTA
+            else
+              ptx::mbar_arrive(tmem_empty_bar(as));
+          }
           as ^= 1;
           if (as == 0) aphase ^= 1u;
           continue;
@@ -469,7 +514,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     make_float4(p.alpha * __uint_as_float(r[qq * 4]), p.alpha * __uint_as_float(r[qq * 4 + 1]),
                                 p.alpha * __uint_as_float(r[qq * 4 + 2]), p.alpha * __uint_as_float(r[qq * 4 + 3]));
               __syncwarp();
-              const int64_t row0 = int64_t(m_blk) * BLOCK_M + q * 32;
+              const int64_t row0 = tile_row0 + q * 32;
               const int owner = int(row0 / p.rs_rows);   // a 128-row tile never straddles two shards
               float* dst0 = static_cast<float*>(p.rs_dst[owner]) + (row0 - owner * p.rs_rows) * p.ldc + col0 + (lane & 7) * 4;
               const bool col_ok = col0 + (lane & 7) * 4 < p.N;
@@ -497,7 +542,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tmem_empty_bar(as));
+      if (lane == 0) {
+            if constexpr (CG == 2)
+              ptx::mbar_arrive_leader(tmem_empty_bar(as));   // the MMA issuer lives in the even CTA
+            else
+              ptx::mbar_arrive(tmem_empty_bar(as));
+          }
       as ^= 1;
       if (as == 0) aphase ^= 1u;
     }
@@ -505,10 +555,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2)
+    ptx::cluster_sync();   // neither CTA of a pair may free its TMEM / exit while the other still signals it
+  else
+    __syncthreads();
   if (warp_idx == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C_::TMEM_COLS);
+    if constexpr (CG == 2)
+      ptx::tmem_dealloc_2sm(tmem_base, C_::TMEM_COLS);
+    else
+      ptx::tmem_dealloc(tmem_base, C_::TMEM_COLS);
   }
 }
 
@@ -554,10 +610,10 @@ uint32_t env_u32(const char* name, uint32_t dflt) {
   return v ? (uint32_t)strtoul(v, nullptr, 0) : dflt;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, typename TC, bool BATCH = false>
+template <int BLOCK_N, bool A_MN, bool B_MN, typename TC, bool BATCH = false, int CG = 1>
 int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p, const CUtensorMap* tc = nullptr) {
-  using C_ = Cfg<BLOCK_N>;
-  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, TC, BATCH>;
+  using C_ = Cfg<BLOCK_N, CG>;
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, TC, BATCH, CG>;
   static bool attr_done[64] = {};  // per template instantiation and device (the attribute is per device)
   if (!attr_done[ctx->device & 63]) {
     static_assert(C_::SMEM_BYTES <= kSmemLimit && kRsStageBytes <= kEpiStageBytes, "shared memory budget");
@@ -565,6 +621,7 @@ int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
     attr_done[ctx->device & 63] = true;
   }
   p.num_n_blocks = int((p.N + BLOCK_N - 1) / BLOCK_N);
+  if (CG == 2) p.num_m_blocks = int((p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M));   // a CTA pair owns 256 rows
   int num_tiles = p.num_m_blocks * p.num_n_blocks;
   if (BATCH) {
     if (p.batch_reduce) {
@@ -580,15 +637,31 @@ int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
   }
   // persistent grid balanced over the waves the tiles need anyway: 512 tiles on 148 SMs take 4 waves whether 148
   // or 128 CTAs run them, and the 20 SMs left free let a concurrent NCCL all-reduce make progress
-  const int waves = (num_tiles + ctx->sm_count - 1) / ctx->sm_count;
-  int grid = (num_tiles + waves - 1) / waves;
+  const int units = ctx->sm_count / CG;                       // CTAs, or CTA pairs
+  const int waves = (num_tiles + units - 1) / units;
+  int grid = ((num_tiles + waves - 1) / waves) * CG;
   size_t smem = C_::SMEM_BYTES;
   if (p.rs_world) {
     if (BLOCK_N != 256 || sizeof(TC) != 4 || p.N % 4 != 0)
       return nk_set_error(ctx, NK_ERR_UNSUPPORTED, "tcgen05 gemm: reduce-scatter epilogue needs 128x256 tiles, f32, N %% 4 == 0");
   }
   if (!tc || BLOCK_N < 64 || BATCH) p.tma_store = 0;
-  kern<<<grid, kNumThreads, smem, ctx->stream>>>(ta, tb, p.tma_store ? *tc : ta, p);
+  if constexpr (CG == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kNumThreads), cfg.dynamicSmemBytes = smem, cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p.tma_store ? *tc : ta, p);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return nk_set_error(ctx, NK_ERR_CUDA, "launch of gemm_tcgen05 (CTA pairs) failed: %s (M=%lld N=%lld K=%lld grid=%d smem=%zu)",
+                          cudaGetErrorString(e), (long long)p.M, (long long)p.N, (long long)p.K, grid, smem);
+    }
+  } else {
+    kern<<<grid, kNumThreads, smem, ctx->stream>>>(ta, tb, p.tma_store ? *tc : ta, p);
+  }
   ctx->launches++;
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess)
@@ -601,7 +674,9 @@ int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
 template <bool A_MN, bool B_MN, typename TC>
 int launch_bn(nk_ctx* ctx, int block_n, const CUtensorMap& ta, const CUtensorMap& tb, GemmParams& p, const CUtensorMap* tc) {
   switch (block_n) {
-    case 256: return launch_cfg<256, A_MN, B_MN, TC>(ctx, ta, tb, p, tc);
+    case 256:
+      if (p.cta_pairs) return launch_cfg<256, A_MN, B_MN, TC, false, 2>(ctx, ta, tb, p, tc);
+      return launch_cfg<256, A_MN, B_MN, TC>(ctx, ta, tb, p, tc);
     case 128: return launch_cfg<128, A_MN, B_MN, TC>(ctx, ta, tb, p, tc);
     case 64: return launch_cfg<64, A_MN, B_MN, TC>(ctx, ta, tb, p, tc);
     default:
@@ -650,10 +725,10 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   }
   // development knobs (tile sweeps, descriptor sweeps on hardware): the environment is read ONCE per process
   struct Knobs {
-    uint32_t block_n, a_lbo, a_sbo, b_lbo, b_sbo, direct_store;
+    uint32_t block_n, a_lbo, a_sbo, b_lbo, b_sbo, direct_store, single_cta;
     Knobs() : block_n(env_u32("NK_GEMM_BLOCK_N", 0)), a_lbo(env_u32("NK_DESC_A_LBO", 0)), a_sbo(env_u32("NK_DESC_A_SBO", 0)),
               b_lbo(env_u32("NK_DESC_B_LBO", 0)), b_sbo(env_u32("NK_DESC_B_SBO", 0)),
-              direct_store(env_u32("NK_GEMM_DIRECT_STORE", 0)) {}
+              direct_store(env_u32("NK_GEMM_DIRECT_STORE", 0)), single_cta(env_u32("NK_GEMM_SINGLE_CTA", 0)) {}
   };
   static const Knobs knobs;
   if (knobs.block_n) block_n = int(knobs.block_n);
@@ -701,6 +776,9 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   if (knobs.b_lbo) p.b_lbo = knobs.b_lbo;
   if (knobs.b_sbo) p.b_sbo = knobs.b_sbo;
 
+  // CTA pairs (256 x 256 tiles over two SMs) wherever a pair has two live row blocks; the reduce-scatter epilogue and
+  // narrow outputs stay on single CTAs
+  p.cta_pairs = (block_n == 256 && M > BLOCK_M && p.rs_world == 0 && (ctx->sm_count % 2) == 0 && knobs.single_cta == 0) ? 1 : 0;
   CUtensorMap ta, tb;
   int rc;
   if (a_mn)
@@ -711,7 +789,7 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   if (b_mn)
     rc = make_tmap_2d(ctx, &tb, B, K, N, ldb, 64, BLOCK_K);
   else
-    rc = make_tmap_2d(ctx, &tb, B, N, K, ldb, BLOCK_K, (uint32_t)block_n);
+    rc = make_tmap_2d(ctx, &tb, B, N, K, ldb, BLOCK_K, (uint32_t)(p.cta_pairs ? block_n / 2 : block_n));
   if (rc) return rc;
 
   static const char* names[2][2][5] = {
@@ -720,7 +798,9 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
       {{"tcgen05_tt_128x256", "tcgen05_tt_128x128", "tcgen05_tt_128x64", "tcgen05_tt_128x32", "tcgen05_tt_128x16"},
        {"tcgen05_tn_128x256", "tcgen05_tn_128x128", "tcgen05_tn_128x64", "", ""}}};
   const int bi = block_n == 256 ? 0 : block_n == 128 ? 1 : block_n == 64 ? 2 : block_n == 32 ? 3 : 4;
-  ctx->last_gemm_kernel = names[a_mn][b_mn][bi];
+  static const char* pair_names[2][2] = {{"tcgen05_nt_2cta_256x256", "tcgen05_nn_2cta_256x256"},
+                                         {"tcgen05_tt_2cta_256x256", "tcgen05_tn_2cta_256x256"}};
+  ctx->last_gemm_kernel = p.cta_pairs ? pair_names[a_mn][b_mn] : names[a_mn][b_mn][bi];
 
   // staged TMA-store epilogue wherever the output is plain (no accumulate, mask or reduce-scatter) and TMA-addressable
   CUtensorMap tc;
@@ -779,7 +859,7 @@ int nk_gemm_tcgen05_batched(nk_ctx* ctx, int transA, int transB, int64_t M, int6
   p.num_k_blocks = int((K + BLOCK_K - 1) / BLOCK_K);
   p.rs_world = 0, p.m_rot = 0, p.rs_rows = M;
   for (int i = 0; i < 8; ++i) p.rs_dst[i] = nullptr;
-  p.tma_store = 0;
+  p.tma_store = 0, p.cta_pairs = 0;
   p.batch = int(batch), p.a_batched = strideA != 0, p.b_batched = strideB != 0, p.batch_reduce = reduce ? 1 : 0, p.splits = 1;
   p.c_batch_stride = strideC;
   p.a_lbo = a_mn ? BLOCK_K * 128 : 16, p.a_sbo = 1024, p.a_kstep = a_mn ? UMMA_K * 128 : UMMA_K * 2;

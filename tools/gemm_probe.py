@@ -72,7 +72,19 @@ CASES = [
     ("TN", 4096, 4096, 4096, "f32", 1.0, 20), ("NT", 8192, 4096, 1024, "bf16", 0.0, 20),
 ]
 
+# the CTA-pair (cta_group::2) variant: every form, tails in M / N / K, accumulate, then the timed shapes
+PAIR_CASES = [
+    ("NT", 256, 256, 64, "f32", 0.0, 0), ("NT", 512, 512, 512, "f32", 0.0, 0), ("NN", 512, 512, 512, "bf16", 0.0, 0),
+    ("TN", 512, 512, 512, "f32", 0.0, 0), ("TT", 256, 512, 512, "f32", 0.0, 0), ("NT", 300, 300, 200, "bf16", 0.0, 0),
+    ("TN", 200, 520, 136, "f32", 1.0, 0), ("NN", 1000, 264, 72, "bf16", 1.0, 0),
+    ("NT", 4096, 4096, 4096, "bf16", 0.0, 30), ("NN", 4096, 4096, 4096, "bf16", 0.0, 30),
+    ("TN", 4096, 4096, 4096, "f32", 0.0, 30), ("NT", 8192, 4096, 1024, "bf16", 0.0, 30),
+    ("TN", 4096, 4096, 8192, "f32", 0.0, 30),
+]
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pairs":
+        CASES = PAIR_CASES
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         form, M, N, K, cdt = sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6]
         beta = float(sys.argv[7]) if len(sys.argv) > 7 else 0.0
