@@ -728,8 +728,9 @@ def roofline(args, dev, nk, spec, peaks, stream):
                 "frac_of_sustained": round(achieved / peaks["tflops_sustained"], 4),
                 "traffic": measured_traffic("gemm_tc_4096"),
                 "traffic_note": "tensor-bound kernel: DRAM bytes per launch (ncu) vs 96-128 MB of operands + output",
-                "kernel": "gemm_tc_kernel (tcgen05, 128x256x64 tiles); mean of the step's own three 4096^3 launches "
-                          "(NT +bias bf16 out, NN bf16 out, TN f32 out), random operands",
+                "kernel": f"gemm_tc_kernel ({dev.last_gemm_kernel}: tcgen05 cta_group::2, 256x256x64 tiles over CTA pairs, TMA-store "
+                          "epilogue); mean of the step's own three 4096^3 launches (NT +bias bf16 out, NN bf16 out, TN f32 out), "
+                          "random operands",
                 "per_form_ms": {k: round(v, 5) for k, v in forms.items()}, "launches_timed": 3 * iters,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops (burst, {peaks['source']}); sustained {peaks['tflops_sustained']}",
                 "algorithmic_flops_per_launch": 2.0 * n ** 3}

@@ -109,6 +109,77 @@ __global__ void __launch_bounds__(kThreads) col2im_kernel(__nv_bfloat16* __restr
   }
 }
 
+// ---- unit stride / dilation: one block per (sample, channel) plane.  The kh*kw rows (c, i, j) of a channel are CONSECUTIVE
+// rows of colsT, i.e. one contiguous block of kh*kw*L elements, and all of them are shifted views of ONE image plane:
+// stage the small side in shared memory, stream the large side with full 16-byte vectors.
+//   im2col: x plane (h*w) -> shared, then kh*kw*L elements out;   col2im: kh*kw*L elements -> shared, then h*w out.
+constexpr int kPlaneThreads = 256;
+
+__global__ void __launch_bounds__(kPlaneThreads) im2col_plane_kernel(__nv_bfloat16* __restrict__ cols, const __nv_bfloat16* __restrict__ x,
+                                                                     CgDims d, int64_t n0, int64_t nn) {
+  extern __shared__ __align__(16) unsigned short plane[];   // h*w (+ slack) input pixels
+  const int hw = int(d.h * d.w), kk = int(d.kh * d.kw), L = int(d.L), wo = int(d.wo), w = int(d.w), kw = int(d.kw);
+  const int lv_n = L / 8;
+  const int64_t planes = nn * d.cin;
+  for (int64_t pl = blockIdx.x; pl < planes; pl += gridDim.x) {
+    const int64_t ns = pl / d.cin, c = pl - ns * d.cin;
+    const unsigned short* src = reinterpret_cast<const unsigned short*>(x) + ((n0 + ns) * d.cin + c) * hw;
+    __syncthreads();
+    for (int i = threadIdx.x; i < hw; i += kPlaneThreads) plane[i] = __ldg(src + i);
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(cols + (ns * d.K + c * kk) * int64_t(L));
+    for (int idx = threadIdx.x; idx < kk * lv_n; idx += kPlaneThreads) {
+      const int t = idx / lv_n, lv = idx - t * lv_n;
+      const int i = t / kw, j = t - i * kw;
+      const int l0 = lv * 8, p = l0 / wo, q = l0 - p * wo;
+      __align__(16) unsigned short e[8];
+      if (q + 8 <= wo) {
+        const unsigned short* s0 = plane + (p + i) * w + q + j;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = s0[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int l = l0 + k, pp = l / wo, qq = l - pp * wo;
+          e[k] = plane[(pp + i) * w + qq + j];
+        }
+      }
+      dst[idx] = *reinterpret_cast<const uint4*>(e);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPlaneThreads) col2im_plane_kernel(__nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ dcols,
+                                                                     CgDims d, int64_t n0, int64_t nn, float beta) {
+  extern __shared__ __align__(16) unsigned short taps[];    // kh*kw rows of L column gradients
+  const int hw = int(d.h * d.w), kk = int(d.kh * d.kw), L = int(d.L), wo = int(d.wo), ho = int(d.ho), w = int(d.w),
+            kw = int(d.kw), kh = int(d.kh);
+  const int64_t planes = nn * d.cin;
+  for (int64_t pl = blockIdx.x; pl < planes; pl += gridDim.x) {
+    const int64_t ns = pl / d.cin, c = pl - ns * d.cin;
+    const uint4* src = reinterpret_cast<const uint4*>(dcols + (ns * d.K + c * kk) * int64_t(L));
+    __syncthreads();
+    for (int i = threadIdx.x; i < kk * L / 8; i += kPlaneThreads) reinterpret_cast<uint4*>(taps)[i] = __ldcs(src + i);
+    __syncthreads();
+    __nv_bfloat16* out = dx + ((n0 + ns) * d.cin + c) * hw;
+    for (int idx = threadIdx.x; idx < hw; idx += kPlaneThreads) {
+      const int u = idx / w, v = idx - u * w;
+      float acc = 0.f;
+      for (int i = 0; i < kh; ++i) {
+        const int p = u - i;
+        if (p < 0 || p >= ho) continue;
+        for (int j = 0; j < kw; ++j) {
+          const int q = v - j;
+          if (q < 0 || q >= wo) continue;
+          acc += __uint_as_float(uint32_t(taps[(i * kw + j) * L + p * wo + q]) << 16);
+        }
+      }
+      if (beta != 0.f) acc += beta * __bfloat162float(out[idx]);
+      out[idx] = __float2bfloat16_rn(acc);
+    }
+  }
+}
+
 // (Cout, Kp) bf16 copy of the (Cout, K) kernel, zero padded (the GEMM operand rows must be 16-byte multiples)
 __global__ void __launch_bounds__(kThreads) pad_kernel_rows(__nv_bfloat16* __restrict__ wp, const __nv_bfloat16* __restrict__ w,
                                                             int64_t cout, int64_t K, int64_t Kp) {
@@ -160,6 +231,40 @@ struct Scratch {   // stream-ordered temporaries released on scope exit
   }
 };
 
+constexpr size_t kPlaneSmemMax = 96 * 1024;
+inline bool unit_steps(const CgDims& d) { return d.sh == 1 && d.sw == 1 && d.dh == 1 && d.dw == 1; }
+inline int plane_blocks(nk_ctx* ctx, int64_t planes) {
+  const int64_t cap = int64_t(ctx->sm_count) * 8;
+  return int(planes < cap ? planes : cap);
+}
+
+int launch_im2col(nk_ctx* ctx, __nv_bfloat16* cols, const __nv_bfloat16* x, const CgDims& d, int64_t n0, int64_t nn) {
+  const size_t smem = size_t(d.h * d.w + 8) * 2;
+  if (unit_steps(d) && smem <= 48 * 1024) {
+    im2col_plane_kernel<<<plane_blocks(ctx, nn * d.cin), kPlaneThreads, smem, ctx->stream>>>(cols, x, d, n0, nn);
+  } else {
+    im2col_kernel<<<cg_blocks(ctx, nn * d.K * (d.L / 8)), kThreads, 0, ctx->stream>>>(cols, x, d, n0, nn);
+  }
+  NK_LAUNCHED(ctx, "im2col");
+  return NK_OK;
+}
+
+int launch_col2im(nk_ctx* ctx, __nv_bfloat16* dx, const __nv_bfloat16* dcols, const CgDims& d, int64_t n0, int64_t nn, float beta) {
+  const size_t smem = size_t(d.kh * d.kw * d.L) * 2;
+  static bool attr_done[64] = {};
+  if (unit_steps(d) && smem <= kPlaneSmemMax) {
+    if (!attr_done[ctx->device & 63]) {
+      cudaFuncSetAttribute(col2im_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPlaneSmemMax);
+      attr_done[ctx->device & 63] = true;
+    }
+    col2im_plane_kernel<<<plane_blocks(ctx, nn * d.cin), kPlaneThreads, smem, ctx->stream>>>(dx, dcols, d, n0, nn, beta);
+  } else {
+    col2im_kernel<<<cg_blocks(ctx, nn * d.cin * d.h * d.w), kThreads, 0, ctx->stream>>>(dx, dcols, d, n0, nn, beta);
+  }
+  NK_LAUNCHED(ctx, "col2im");
+  return NK_OK;
+}
+
 int64_t chunk_samples(const CgDims& d) {
   int64_t per = d.L * d.Kp * 2;
   int64_t c = kChunkBytes / per;
@@ -186,8 +291,8 @@ int nk_conv_gemm_fwd(nk_ctx* ctx, void* y, const void* x, const void* w, const v
   if (rc) return rc;
   for (int64_t n0 = 0; n0 < n; n0 += cs) {
     const int64_t nn = n - n0 < cs ? n - n0 : cs;
-    im2col_kernel<<<cg_blocks(ctx, nn * d.K * (d.L / 8)), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)s.p[1], (const __nv_bfloat16*)x, d, n0, nn);
-    NK_LAUNCHED(ctx, "im2col");
+    rc = launch_im2col(ctx, (__nv_bfloat16*)s.p[1], (const __nv_bfloat16*)x, d, n0, nn);
+    if (rc) return rc;
     // y[n] (Cout x L) = Wp (Cout x K) . colsT[n] (K x L) : NN, A shared by every sample (TMA zero-fills k >= K)
     rc = nk_gemm_tcgen05_batched(ctx, 0, 0, cout, d.L, d.K, 1.f, s.p[0], d.Kp, 0, s.p[1], d.L, d.K * d.L,
                                  static_cast<__nv_bfloat16*>(y) + n0 * cout * d.L, d.L, cout * d.L, nn, NK_BF16, bias, NK_BF16,
@@ -218,8 +323,8 @@ int nk_conv_gemm_bwd_input(nk_ctx* ctx, void* dx, const void* g, const void* w, 
                                  static_cast<const __nv_bfloat16*>(g) + n0 * cout * d.L, d.L, cout * d.L, s.p[1], d.L, d.K * d.L, nn,
                                  NK_BF16, nullptr, NK_BF16, 0, 0);
     if (rc) return rc;
-    col2im_kernel<<<cg_blocks(ctx, nn * cin * h * wd), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)dx, (const __nv_bfloat16*)s.p[1], d, n0, nn, beta);
-    NK_LAUNCHED(ctx, "col2im");
+    rc = launch_col2im(ctx, (__nv_bfloat16*)dx, (const __nv_bfloat16*)s.p[1], d, n0, nn, beta);
+    if (rc) return rc;
   }
   ctx->last_conv_kernel = "tcgen05_im2col_gemm_dx";
   return NK_OK;
@@ -239,8 +344,8 @@ int nk_conv_gemm_bwd_kernel(nk_ctx* ctx, void* dwt, int dw_dtype, const void* g,
   if (rc) return rc;
   for (int64_t n0 = 0; n0 < n; n0 += cs) {
     const int64_t nn = n - n0 < cs ? n - n0 : cs;
-    im2col_kernel<<<cg_blocks(ctx, nn * d.K * (d.L / 8)), kThreads, 0, ctx->stream>>>((__nv_bfloat16*)s.p[1], (const __nv_bfloat16*)x, d, n0, nn);
-    NK_LAUNCHED(ctx, "im2col");
+    rc = launch_im2col(ctx, (__nv_bfloat16*)s.p[1], (const __nv_bfloat16*)x, d, n0, nn);
+    if (rc) return rc;
     // acc (Cout x K) += sum_n G[n] (Cout x L) . colsT[n]^T (L x K) : NT, reduced over the samples inside the k loop
     rc = nk_gemm_tcgen05_batched(ctx, 0, 1, cout, d.K, d.L, 1.f, static_cast<const __nv_bfloat16*>(g) + n0 * cout * d.L, d.L,
                                  cout * d.L, s.p[1], d.L, d.K * d.L, s.p[2], d.Kp, 0, nn, NK_F32, nullptr, NK_F32, 0, 1);

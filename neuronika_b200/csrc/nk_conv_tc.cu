@@ -1199,6 +1199,7 @@ constexpr int kFThreads = 768;  // warp 0: MMA + TMEM alloc, 1: TMA (x windows),
                                 // 8..15: dX pixel warps (warp 8 + w reads TMEM lane quarter w % 4), 16..23: cp.async G loaders
 constexpr int kFShiftWarp0 = 4, kFPixelWarp0 = 8, kFLoadWarp0 = 16;
 constexpr int kFDxCols = 64;    // TMEM columns of one dX row tile: 2 pixel halves x 32 tap columns
+constexpr int kFDxBufs = 4;     // dX row tiles in flight in TMEM (4 x 64 columns; the dW accumulators sit behind them)
 
 struct ConvBP {
   int n, cin, h, w, cout, ho, wo;
@@ -1228,11 +1229,16 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   // layout: [dX weights kblocks x 4 KB: B operand, 32 tap rows x 64 output channels, K-major]
   //         [stages x 4 chunks x (G slot Cout x 128 B | X slots ksteps x 2 KB | halo 1 KB)]
   //         [boundary exchange: 2 parities x 8 warps x 2 pixels x 32 floats][barriers]
+  // uniform output gradient: ONE constant G tile (4 chunks) shared by every stage instead of a G slot per stage, so a
+  // stage is only the x windows (28 KB instead of 61 KB at config 3: 7 rows in flight instead of 3)
   const uint32_t g_bytes = p.cout * 128;
   const uint32_t x_bytes = p.ksteps * 2048;
-  const uint32_t chunk_bytes = g_bytes + x_bytes + 1024;
+  const uint32_t g_in_chunk = p.use_const ? 0u : g_bytes;          // bytes of G in front of the x slots of a chunk
+  const uint32_t chunk_bytes = g_in_chunk + x_bytes + 1024;
   const uint32_t stage_bytes = kChunksPerTile * chunk_bytes;
-  const uint32_t st_off = p.kblocks * 4096;
+  const uint32_t gconst_off = p.kblocks * 4096;
+  const uint32_t st_off = gconst_off + (p.use_const ? kChunksPerTile * g_bytes : 0u);
+  const uint32_t g_stride = p.use_const ? g_bytes : chunk_bytes;   // distance between the G tiles of consecutive chunks
   const uint32_t h_off = st_off + p.stages * stage_bytes;
   const uint32_t h_bytes = 2 * 8 * 2 * 32 * 4;
   const uint32_t bar_off = h_off + h_bytes;
@@ -1242,9 +1248,15 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   auto ready_bar = [&](int s) { return bar_base + 8u * (S + s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
   auto d_full_bar = [&](int d) { return bar_base + 8u * (3 * S + d); };
-  auto d_empty_bar = [&](int d) { return bar_base + 8u * (3 * S + 2 + d); };
-  const uint32_t done_bar = bar_base + 8u * (3 * S + 4), tmem_slot = done_bar + 8;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (3 * S + 5));
+  auto d_empty_bar = [&](int d) { return bar_base + 8u * (3 * S + kFDxBufs + d); };
+  const uint32_t done_bar = bar_base + 8u * (3 * S + 2 * kFDxBufs), tmem_slot = done_bar + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8u * (3 * S + 2 * kFDxBufs + 1));
+  // waits of roles with stages of slack back off between polls (issue slots for the working warps); NK_CONV_DBG bit 32
+  // times the kernel with plain hardware-suspended waits everywhere
+  auto wait_slack = [&](uint32_t bar, uint32_t parity) {
+    if (p.dbg & 32) ptx::mbar_wait(bar, parity);
+    else ptx::mbar_wait_relaxed(bar, parity);
+  };
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   {
@@ -1264,18 +1276,17 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     for (int i = threadIdx.x; i < S * kChunksPerTile * 32; i += kFThreads) {
       const int sc = i / 32, wq = i % 32;
       const int s = sc / kChunksPerTile, c = sc % kChunksPerTile;
-      *reinterpret_cast<uint32_t*>(base_ptr + st_off + s * stage_bytes + c * chunk_bytes + g_bytes + 15 * 128 + wq * 4) =
+      *reinterpret_cast<uint32_t*>(base_ptr + st_off + s * stage_bytes + c * chunk_bytes + g_in_chunk + 15 * 128 + wq * 4) =
           0x3F803F80u;
     }
   }
   if (p.use_const) {
     // uniform output gradient: the G tile is the same for every row -- written ONCE into every stage (value inside the
     // row, zero beyond Wo), never fetched and never rewritten; the loader warps have nothing to do per row
-    for (int i = threadIdx.x; i < S * kChunksPerTile * p.cout * 32; i += kFThreads) {
-      const int wq = i & 31, o = (i >> 5) % p.cout, sc = (i >> 5) / p.cout;
-      const int s = sc / kChunksPerTile, c = sc % kChunksPerTile;
+    for (int i = threadIdx.x; i < kChunksPerTile * p.cout * 32; i += kFThreads) {
+      const int wq = i & 31, o = (i >> 5) % p.cout, c = (i >> 5) / p.cout;
       const uint32_t val = (p.wo - c * kChunk - wq * 2) > 0 ? p.const_bits : 0u;
-      *reinterpret_cast<uint32_t*>(base_ptr + st_off + s * stage_bytes + c * chunk_bytes + o * 128 +
+      *reinterpret_cast<uint32_t*>(base_ptr + gconst_off + c * g_bytes + o * 128 +
                                    ((((wq >> 2) ^ (o & 7)) << 4) + (wq & 3) * 4)) = val;
     }
   }
@@ -1287,7 +1298,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       ptx::mbar_init(ready_bar(s), p.use_const ? 4 : 256 + 4);
       ptx::mbar_init(empty_bar(s), 1);
     }
-    for (int d = 0; d < 2; ++d) {
+    for (int d = 0; d < kFDxBufs; ++d) {
       ptx::mbar_init(d_full_bar(d), 1);
       ptx::mbar_init(d_empty_bar(d), 8);   // the 8 pixel warps
     }
@@ -1303,7 +1314,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tmem_dw = tmem_base + 2u * kFDxCols;   // dW accumulators behind the two dX buffers
+  const uint32_t tmem_dw = tmem_base + uint32_t(kFDxBufs * kFDxCols);   // dW accumulators behind the dX buffers
 
   // every role walks the same sequence of (unit, G row) tiles; G row pr feeds dW only when the unit owns it (pr >= u0)
   auto unit_rows = [&](int unit, int& n, int& u0, int& u1, int& p_lo, int& p_hi) {
@@ -1331,23 +1342,24 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           ptx::mbar_wait(d_empty_bar(db), dphase ^ 1u);
           ptx::tc_fence_after();
           const uint32_t sb = base + st_off + stage * stage_bytes;
-          // dX (transposed): pixel half hf = chunks 2hf, 2hf+1 as the MN-major A operand (64-px atoms chunk_bytes apart)
+          const uint32_t gb = p.use_const ? base + gconst_off : sb;   // G tile of chunk c at gb + c * g_stride
+          // dX (transposed): pixel half hf = chunks 2hf, 2hf+1 as the MN-major A operand (64-px atoms g_stride apart)
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             const uint32_t tmem_d = tmem_base + uint32_t(db * kFDxCols + hf * 32);
             for (int ks = 0; ks < ((p.dbg & 2) ? 0 : p.cout / 16); ++ks) {
-              const uint64_t adesc = ptx::make_smem_desc_sw128(sb + 2 * hf * chunk_bytes + ks * 2048, chunk_bytes, 1024);
+              const uint64_t adesc = ptx::make_smem_desc_sw128(gb + 2 * hf * g_stride + ks * 2048, g_stride, 1024);
               const uint64_t bdesc = ptx::make_smem_desc_sw128(base + (ks >> 2) * 4096 + (ks & 3) * 32, 16, 1024);
               ptx::mma_f16_ss(tmem_d, adesc, bdesc, idesc_dx, ks != 0 ? 1u : 0u);
             }
           }
           ptx::mma_commit(d_full_bar(db));
-          db ^= 1;
+          db = (db + 1) & (kFDxBufs - 1);
           if (db == 0) dphase ^= 1u;
           if (pr >= u0 && !(p.dbg & 1)) {
             for (int c = 0; c < p.cpr; ++c) {
-              const uint64_t adesc = ptx::make_smem_desc_sw128(sb + c * chunk_bytes, 16, 1024);
-              const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + c * chunk_bytes + g_bytes, 16, 1024);
+              const uint64_t adesc = ptx::make_smem_desc_sw128(gb + c * g_stride, 16, 1024);
+              const uint64_t bdesc = ptx::make_smem_desc_sw128(sb + c * chunk_bytes + g_in_chunk, 16, 1024);
 #pragma unroll
               for (int kq = 0; kq < 4; ++kq) {
                 const uint32_t a = (cnt++) & uint32_t(p.nacc - 1);
@@ -1375,11 +1387,11 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         int n, u0, u1, p_lo, p_hi;
         unit_rows(unit, n, u0, u1, p_lo, p_hi);
         for (int pr = p_lo; pr <= p_hi; ++pr) {
-          ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
+          wait_slack(empty_bar(stage), phase ^ 1u);
           if (pr >= u0 && !(p.dbg & 16)) {
             ptx::mbar_expect_tx(fullx_bar(stage), tx);
             for (int c = 0; c < p.cpr; ++c) {
-              const uint32_t sc = base + st_off + stage * stage_bytes + c * chunk_bytes + g_bytes;
+              const uint32_t sc = base + st_off + stage * stage_bytes + c * chunk_bytes + g_in_chunk;
               for (int grp = 0; grp < p.ng; ++grp) {
                 ptx::tma_load_4d(sc + grp * 2048, &tmap_x, fullx_bar(stage), c * kChunk, pr, grp * p.cpg, n);
                 ptx::tma_load_4d(sc + x_bytes + grp * 256, &tmap_halo, fullx_bar(stage), (c + 1) * kChunk, pr,
@@ -1408,12 +1420,12 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       int n, u0, u1, p_lo, p_hi;
       unit_rows(unit, n, u0, u1, p_lo, p_hi);
       for (int pr = p_lo; pr <= p_hi; ++pr) {
-        ptx::mbar_wait_relaxed(fullx_bar(stage), phase);
+        wait_slack(fullx_bar(stage), phase);
         if (pr >= u0 && !(p.dbg & 8)) {
           any_owned = true;  // at least one dW chain ran: every accumulator has been written (>= 4 UMMAs >= nacc)
           uint8_t* sp = base_ptr + st_off + stage * stage_bytes;
           for (int c = 0; c < p.cpr; ++c) {
-            uint8_t* xs = sp + c * chunk_bytes + g_bytes;
+            uint8_t* xs = sp + c * chunk_bytes + g_in_chunk;
             const uint8_t* halo = xs + x_bytes;
             for (int grp = 0; grp < p.ng; ++grp)
               for (int q = wrp; q < pairs; q += 4) {
@@ -1486,7 +1498,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       int n, u0, u1, p_lo, p_hi;
       unit_rows(unit, n, u0, u1, p_lo, p_hi);
       for (int pr = p_lo; pr <= p_hi; ++pr) {
-        ptx::mbar_wait_relaxed(empty_bar(stage), phase ^ 1u);
+        wait_slack(empty_bar(stage), phase ^ 1u);
         const uint32_t sb = base + st_off + stage * stage_bytes;
         const __nv_bfloat16* grow = p.g + (long long)n * p.cout * plane + (long long)pr * p.wo;
         if (base8 && (((long long)pr * p.wo) & 3) == 0) {
@@ -1559,7 +1571,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
       };
       for (int pr = p_lo; pr <= p_hi; ++pr) {
-        ptx::mbar_wait_relaxed(d_full_bar(db), dphase);
+        wait_slack(d_full_bar(db), dphase);
         ptx::tc_fence_after();
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t((pw & 3) * 32) << 16) + uint32_t(db * kFDxCols + (pw >> 2) * 32), r);
@@ -1567,7 +1579,7 @@ conv_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(d_empty_bar(db));
-        db ^= 1;
+        db = (db + 1) & (kFDxBufs - 1);
         if (db == 0) dphase ^= 1u;
         if (p.dbg & 4) continue;
         // publish the two last pixels of this warp for the next warp's lanes 0 and 1
@@ -1658,12 +1670,14 @@ int nk_conv2d_bwd_fused_tc(nk_ctx* ctx, void* dx, float beta_dx, void* dwt, int 
   p.cpr = (p.wo + kChunk - 1) / kChunk;
   while (p.nacc > p.cpr * 4) p.nacc /= 2;   // one owned row (4 UMMAs per live chunk) must touch every accumulator
   p.kblocks = (p.cout + 63) / 64;
-  const size_t stage_bytes = size_t(kChunksPerTile) * (p.cout * 128 + p.ksteps * 2048 + 1024);
+  // uniform gradient: one constant G tile for all stages (a stage holds x windows only)
+  const size_t g_tile = size_t(kChunksPerTile) * p.cout * 128;
+  const size_t stage_bytes = size_t(kChunksPerTile) * ((p.use_const ? 0 : p.cout * 128) + p.ksteps * 2048 + 1024);
   const size_t h_bytes = 2 * 8 * 2 * 32 * 4;   // boundary exchange of the pixel warps
-  const size_t fixed = 1024 + size_t(p.kblocks) * 4096 + h_bytes + 512;
+  const size_t fixed = 1024 + size_t(p.kblocks) * 4096 + (p.use_const ? g_tile : 0) + h_bytes + 512;
   if (fixed + 2 * stage_bytes > 232448) return NK_ERR_UNSUPPORTED;
   p.stages = int((232448 - fixed) / stage_bytes);
-  if (p.stages > 4) p.stages = 4;
+  if (p.stages > (p.use_const ? 6 : 4)) p.stages = p.use_const ? 6 : 4;
   p.rb = 56;
   if (p.h < 2 * p.rb) p.rb = p.h;
   p.blocks_per_img = (p.h + p.rb - 1) / p.rb;
