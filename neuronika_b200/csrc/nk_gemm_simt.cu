@@ -225,16 +225,56 @@ __device__ __forceinline__ void store4(T* p, bool vec, int valid, const float* v
   }
 }
 
+// raw 4-element group of a row (8 bytes of bf16 / 16 bytes of f32) kept as loaded: conversion happens at use, so that
+// eight rows' worth of mask / old values can be in flight without eight rows' worth of converted registers
+template <typename T>
+struct Raw4 {
+  uint32_t w[sizeof(T) == 2 ? 2 : 4];
+};
+template <typename T>
+__device__ __forceinline__ Raw4<T> load_raw4(const T* p, bool vec, int valid) {
+  Raw4<T> r;
+  if (vec) {
+    if constexpr (sizeof(T) == 2) {
+      const uint2 v = *reinterpret_cast<const uint2*>(p);
+      r.w[0] = v.x, r.w[1] = v.y;
+    } else {
+      const uint4 v = *reinterpret_cast<const uint4*>(p);
+      r.w[0] = v.x, r.w[1] = v.y, r.w[2] = v.z, r.w[3] = v.w;
+    }
+  } else {
+    float f[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f[j] = j < valid ? nk_to_f32<T>(p[j]) : 0.f;
+    if constexpr (sizeof(T) == 2) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(f[0], f[1]), hi = __floats2bfloat162_rn(f[2], f[3]);   // exact: they were bf16
+      r.w[0] = *reinterpret_cast<uint32_t*>(&lo), r.w[1] = *reinterpret_cast<uint32_t*>(&hi);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r.w[j] = __float_as_uint(f[j]);
+    }
+  }
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ float raw_get(const Raw4<T>& r, int j) {
+  if constexpr (sizeof(T) == 2) return __uint_as_float((j & 1) ? (r.w[j >> 1] & 0xffff0000u) : (r.w[j >> 1] << 16));
+  else return __uint_as_float(r.w[j]);
+}
+
 template <typename TAB, typename TC, int KP>
-__global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
+__global__ void __launch_bounds__(256, 2) gemm_small_k_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
                                                            TC* __restrict__ C, int64_t M, int64_t N, int K,
                                                            int64_t lda, int64_t ldb, int64_t ldc, Epilogue ep) {
-  // block: 32 rows x 1024 columns; thread: 4 consecutive columns of all 32 rows, 4 rows in flight at a time so that
-  // the (optional) read of C and the stores overlap; every access to C is one 8/16-byte vector
-  __shared__ float As[32][KP];   // KP = K rounded up to 4: bounds the FMAs (10 -> 12, not 16)
-  const int64_t m0 = int64_t(blockIdx.y) * 32;
+  // block: 64 rows x 1024 columns; thread: 4 consecutive columns of all rows, 8 rows in flight at a time so that the
+  // (optional) reads of the mask / old C overlap the arithmetic; every access to C is one 8/16-byte vector.  The FMAs are
+  // the packed two-lane form (fma.rn.f32x2, same IEEE result per lane): the kernel is issue bound, K x 4 FMAs per
+  // 8 bytes stored -- KP = K rounded up to 4 bounds them (10 -> 12, not 16).
+  constexpr int kRows = 64, kFlight = 8;
+  __shared__ __align__(16) float As[kRows][KP];
+  const int64_t m0 = int64_t(blockIdx.y) * kRows;
   const int64_t n = (int64_t(blockIdx.x) * 256 + threadIdx.x) * 4;
-  for (int i = threadIdx.x; i < 32 * KP; i += 256) {
+  for (int i = threadIdx.x; i < kRows * KP; i += 256) {
     const int r = i / KP, k = i - r * KP;
     As[r][k] = (k < K && m0 + r < M) ? nk_to_f32<TAB>(A[(m0 + r) * lda + k]) : 0.f;
   }
@@ -244,11 +284,12 @@ __global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict
   const bool vb = valid == 4 && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
   const bool vc = valid == 4 && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
   const bool vmask = vc && ((reinterpret_cast<uintptr_t>(ep.mask) & 15) == 0);
-  float b[KP][4];
+  float2 b01[KP], b23[KP];
 #pragma unroll
   for (int k = 0; k < KP; ++k) {
-    if (k < K) load4<TAB>(B + int64_t(k) * ldb + n, vb, valid, b[k]);
-    else b[k][0] = b[k][1] = b[k][2] = b[k][3] = 0.f;
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k < K) load4<TAB>(B + int64_t(k) * ldb + n, vb, valid, t);
+    b01[k] = make_float2(t[0], t[1]), b23[k] = make_float2(t[2], t[3]);
   }
   float bias[4] = {0.f, 0.f, 0.f, 0.f};
   if (ep.bias) {
@@ -258,34 +299,40 @@ __global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict
         bias[j] = ep.bias_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(ep.bias)[n + j])
                                : static_cast<const float*>(ep.bias)[n + j];
   }
-  const int rows = int(M - m0 < 32 ? M - m0 : 32);
-  for (int r0 = 0; r0 < rows; r0 += 4) {
-    float old[4][4], msk[4][4];
+  const int rows = int(M - m0 < kRows ? M - m0 : kRows);
+  for (int r0 = 0; r0 < rows; r0 += kFlight) {
+    Raw4<TC> old[kFlight], msk[kFlight];
     if (ep.beta != 0.f) {
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr)
-        if (r0 + rr < rows) load4<TC>(C + (m0 + r0 + rr) * ldc + n, vc, valid, old[rr]);
+      for (int rr = 0; rr < kFlight; ++rr)
+        if (r0 + rr < rows) old[rr] = load_raw4<TC>(C + (m0 + r0 + rr) * ldc + n, vc, valid);
     }
     if (ep.mask) {
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr)
-        if (r0 + rr < rows) load4<TC>(static_cast<const TC*>(ep.mask) + (m0 + r0 + rr) * ldc + n, vmask, valid, msk[rr]);
+      for (int rr = 0; rr < kFlight; ++rr)
+        if (r0 + rr < rows) msk[rr] = load_raw4<TC>(static_cast<const TC*>(ep.mask) + (m0 + r0 + rr) * ldc + n, vmask, valid);
     }
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
+    for (int rr = 0; rr < kFlight; ++rr) {
       if (r0 + rr >= rows) break;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < KP; ++k) {
-        const float a = As[r0 + rr][k];  // zero for k >= K
+      for (int k4 = 0; k4 < KP / 4; ++k4) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[r0 + rr][k4 * 4]);  // zero for k >= K
+        const float a[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, b[k][j], acc[j]);
+        for (int i = 0; i < 4; ++i) {
+          const float2 aa = make_float2(a[i], a[i]);
+          a01 = __ffma2_rn(aa, b01[k4 * 4 + i], a01);
+          a23 = __ffma2_rn(aa, b23[k4 * 4 + i], a23);
+        }
       }
+      float acc[4] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float v = ep.alpha * acc[j];
-        if (ep.mask) v = msk[rr][j] > 0.f ? v : 0.f;
-        if (ep.beta != 0.f) v += ep.beta * old[rr][j];
+        if (ep.mask) v = raw_get<TC>(msk[rr], j) > 0.f ? v : 0.f;
+        if (ep.beta != 0.f) v += ep.beta * raw_get<TC>(old[rr], j);
         v += bias[j];
         if (ep.relu) v = v > 0.f ? v : 0.f;
         acc[j] = v;
@@ -297,16 +344,18 @@ __global__ void __launch_bounds__(256) gemm_small_k_kernel(const TAB* __restrict
 
 // small-M: block = 8 warps x 128 columns (lane: 4 consecutive) x one slab of k.  Warp w takes the rows k = w, w + 8, ...
 // of the slab with eight 8/16-byte loads of the streamed operand in flight; the M (<= 16) values of A for a row come
-// from shared memory as broadcast 16-byte reads; MP = M rounded up to 4 bounds the FMAs (10 -> 12, not 16).  The eight
-// warps' partial sums meet in shared memory, so a block ends with M x 128 global atomics instead of M x 512 per 128
-// threads: at 10 x 4096 x 8192 the first version (one warp-slab per block) took 94 us, 6x its FMA / HBM floor.
+// from shared memory as broadcast 16-byte reads; MP = M rounded up to 4 bounds the FMAs (10 -> 12, not 16), which are
+// the packed two-lane form.  The eight warps' partial sums meet in a three-round tree through shared memory (shared
+// f32 atomicAdd is a compare-and-swap loop in SASS, ATOMS.CAST.SPIN: 8-way contended it cost more than the loop), and
+// one warp ends the block with M x 128 global reductions.
 constexpr int kSmChunk = 256;   // rows of A staged per pass
 template <typename TAB, int MP>
 __global__ void __launch_bounds__(256) gemm_small_m_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
                                                            float* __restrict__ scratch, int M, int64_t N, int64_t K,
                                                            int64_t lda, int64_t ldb, int64_t k_per_block) {
-  __shared__ __align__(16) float As[kSmChunk][MP];
-  __shared__ float red[MP][128];
+  constexpr int kAsFloats = kSmChunk * MP, kRedFloats = 4 * MP * 128;
+  __shared__ __align__(16) float smem[kAsFloats > kRedFloats ? kAsFloats : kRedFloats];
+  float (*As)[MP] = reinterpret_cast<float (*)[MP]>(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n = int64_t(blockIdx.x) * 128 + lane * 4;
   const int64_t k_begin = int64_t(blockIdx.y) * k_per_block;
@@ -314,12 +363,9 @@ __global__ void __launch_bounds__(256) gemm_small_m_kernel(const TAB* __restrict
   if (k_end > K) k_end = K;
   const int valid = n < N ? int(N - n < 4 ? N - n : 4) : 0;
   const bool vb = valid == 4 && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
-  float acc[MP][4];
+  float2 acc01[MP], acc23[MP];
 #pragma unroll
-  for (int m = 0; m < MP; ++m)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
-  for (int i = threadIdx.x; i < MP * 128; i += 256) (&red[0][0])[i] = 0.f;
+  for (int m = 0; m < MP; ++m) acc01[m] = make_float2(0.f, 0.f), acc23[m] = make_float2(0.f, 0.f);
   for (int64_t k0 = k_begin; k0 < k_end; k0 += kSmChunk) {
     __syncthreads();
     const int rows = int(k_end - k0 < kSmChunk ? k_end - k0 : kSmChunk);
@@ -339,29 +385,50 @@ __global__ void __launch_bounds__(256) gemm_small_m_kernel(const TAB* __restrict
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int r = kb + 8 * u < rows ? kb + 8 * u : 0;   // (bv is zero beyond the slab)
+          const float2 b01 = make_float2(bv[u][0], bv[u][1]), b23 = make_float2(bv[u][2], bv[u][3]);
 #pragma unroll
           for (int m4 = 0; m4 < MP / 4; ++m4) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[r][m4 * 4]);
             const float a[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) acc[m4 * 4 + i][j] = fmaf(a[i], bv[u][j], acc[m4 * 4 + i][j]);
+            for (int i = 0; i < 4; ++i) {
+              const float2 aa = make_float2(a[i], a[i]);
+              acc01[m4 * 4 + i] = __ffma2_rn(aa, b01, acc01[m4 * 4 + i]);
+              acc23[m4 * 4 + i] = __ffma2_rn(aa, b23, acc23[m4 * 4 + i]);
+            }
           }
         }
       }
     }
   }
-  __syncthreads();
+  // tree over the 8 warps: the upper half of the live warps stores, the lower half adds
+  float4* red = reinterpret_cast<float4*>(smem);            // [4 warps][MP][32 lanes] float4, aliases As (no longer needed)
 #pragma unroll
-  for (int m = 0; m < MP; ++m)
+  for (int half = 4; half >= 1; half >>= 1) {
+    __syncthreads();
+    if (warp >= half && warp < 2 * half) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(&red[m][lane * 4 + j], acc[m][j]);
-  __syncthreads();
-  const int64_t nb = int64_t(blockIdx.x) * 128;
-  for (int i = threadIdx.x; i < M * 128; i += 256) {
-    const int m = i >> 7, c = i & 127;
-    if (nb + c < N) atomicAdd(&scratch[int64_t(m) * N + nb + c], red[m][c]);
+      for (int m = 0; m < MP; ++m)
+        red[((warp - half) * MP + m) * 32 + lane] = make_float4(acc01[m].x, acc01[m].y, acc23[m].x, acc23[m].y);
+    }
+    __syncthreads();
+    if (warp < half) {
+#pragma unroll
+      for (int m = 0; m < MP; ++m) {
+        const float4 v = red[(warp * MP + m) * 32 + lane];
+        acc01[m].x += v.x, acc01[m].y += v.y, acc23[m].x += v.z, acc23[m].y += v.w;
+      }
+    }
+  }
+  if (warp == 0 && valid) {
+#pragma unroll
+    for (int m = 0; m < MP; ++m) {
+      if (m >= M) break;
+      const float v[4] = {acc01[m].x, acc01[m].y, acc23[m].x, acc23[m].y};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < valid) atomicAdd(&scratch[int64_t(m) * N + n + j], v[j]);
+    }
   }
 }
 
@@ -370,7 +437,7 @@ int launch_skinny(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int
                   const void* B, int64_t ldb, void* C, int64_t ldc, Epilogue ep, bool* handled) {
   *handled = false;
   if (!transA && !transB && K <= kSkinnyMax && K > 0 && N >= 256) {
-    dim3 grid((unsigned)((N + 1023) / 1024), (unsigned)((M + 31) / 32));
+    dim3 grid((unsigned)((N + 1023) / 1024), (unsigned)((M + 63) / 64));
     if (grid.y > 65535) return NK_OK;
 #define NK_SK(KP_) gemm_small_k_kernel<TAB, TC, KP_><<<grid, 256, 0, ctx->stream>>>((const TAB*)A, (const TAB*)B, (TC*)C, M, N, (int)K, lda, ldb, ldc, ep)
     if (K <= 4)
@@ -426,7 +493,7 @@ int launch_skinny(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int
 // backward of the layer below applied on the way out.  NK_ERR_UNSUPPORTED (nothing done) for every other shape.
 int nk_gemm_simt_small_k_masked(nk_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                                 int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype, const void* mask) {
-  if (K > kSkinnyMax || K <= 0 || N < 256 || (M + 31) / 32 > 65535) return NK_ERR_UNSUPPORTED;
+  if (K > kSkinnyMax || K <= 0 || N < 256 || (M + 63) / 64 > 65535) return NK_ERR_UNSUPPORTED;
   Epilogue ep{1.f, beta, nullptr, 0, 0, mask};
   bool handled = false;
   int rc;

@@ -776,9 +776,10 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   if (knobs.b_lbo) p.b_lbo = knobs.b_lbo;
   if (knobs.b_sbo) p.b_sbo = knobs.b_sbo;
 
-  // CTA pairs (256 x 256 tiles over two SMs) wherever a pair has two live row blocks; the reduce-scatter epilogue and
-  // narrow outputs stay on single CTAs
-  p.cta_pairs = (block_n == 256 && M > BLOCK_M && p.rs_world == 0 && (ctx->sm_count % 2) == 0 && knobs.single_cta == 0) ? 1 : 0;
+  // CTA pairs (256 x 256 tiles over two SMs) wherever a pair has two live row blocks (with the reduce-scatter epilogue:
+  // when the 256 rows of a pair belong to one owner); narrow outputs stay on single CTAs
+  p.cta_pairs = (block_n == 256 && M > BLOCK_M && (ctx->sm_count % 2) == 0 && knobs.single_cta == 0 &&
+                 (p.rs_world == 0 || M % (int64_t(p.rs_world) * 2 * BLOCK_M) == 0)) ? 1 : 0;   // a pair's 256 rows: one owner
   CUtensorMap ta, tb;
   int rc;
   if (a_mn)

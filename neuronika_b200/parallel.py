@@ -294,6 +294,15 @@ class FusedGradientExchange:
         self.slots = PeerMemory(device, max(off, 4) * 4, world, rank)
         # receive slots of the small all-reduce: world copies of every non-fused element
         small_total = self.layout.total - off
+        # every non-fused parameter has its own receive region (offsets in floats, 16-byte aligned), so that its all-reduce
+        # can be issued the moment its gradient is final instead of in one bulk call at the end of backward
+        self.small_off = {}
+        cur = 0
+        for i, sh in enumerate(self.layout.shapes):
+            if i not in self.fused:
+                self.small_off[i] = cur
+                cur += (int(np.prod(sh)) + 3) // 4 * 4
+        small_total = max(small_total, cur)
         self.small_slots = PeerMemory(device, max(small_total, 4) * 4 * world, world, rank)
         self.flags = PeerMemory(device, 1024, world, rank)          # words [0,16): exchange, [64,80): small all-reduce
         self.state = CuArray(device, (16,), F32)                    # zero-filled local words: ExState x 2
@@ -323,7 +332,22 @@ class FusedGradientExchange:
                 p.set_grad_rs(self.world, self.rank, [int(v) for v in table],
                               lambda pushed, pi=pi: self._pushed(pi, pushed))
             else:
-                p.set_grad_hook(lambda b, e, off=lay.offsets[pi]: self.ranges.add(off + b, off + e))
+                p.set_grad_hook(lambda b, e, pi=pi: self._small_ready(pi, b, e))
+
+    def _small_ready(self, pi: int, b: int, e: int) -> None:
+        """gradient-ready hook of a non-fused parameter (called inside backward between two launches): record an event;
+        the all-reduce itself is enqueued at the next hook / wait(), on the side stream, where it overlaps the rest of
+        backward instead of queueing behind the big matrices' exchanges at the end"""
+        self._flush_pending()
+        lay = self.layout
+        n = int(np.prod(lay.shapes[pi]))
+        if (b, e) != (0, n) or n > self.SMALL_MAX:          # partial delivery or too big for the peer-memory kernel
+            self.ranges.add(lay.offsets[pi] + b, lay.offsets[pi] + e)
+            return
+        ev = self._events[self._ev_i % len(self._events)]
+        self._ev_i += 1
+        ev.record(self.compute)
+        self._pending.append((ev, pi))
 
     def detach(self) -> None:
         """Remove the exchange plans and hooks from the parameters (gradients stay local afterwards)."""
@@ -359,6 +383,13 @@ class FusedGradientExchange:
         lay = self.layout
         for ev, pi in pending:
             self.comm.wait_event(ev)
+            if pi not in self.fused:                        # small tensor: single-CTA all-reduce through peer memory
+                n = int(np.prod(lay.shapes[pi]))
+                L.check(L.lib.nk_peer_allreduce_small(self.comm_device.ctx, C.c_void_p(self.bucket_mem.local + lay.offsets[pi] * 4),
+                                                      self.small_slots.offset_table(self.small_off[pi] * self.world * 4),
+                                                      self.flags.offset_table(256), self.world, self.rank, n,
+                                                      C.c_void_p(self.state.ptr.value + 16)), self.comm_device.ctx)
+                continue
             shard = int(np.prod(lay.shapes[pi])) // self.world
             grads = self.bucket_mem.offset_table(lay.offsets[pi] * 4)
             slots_local = self.slots.local + self.slot_off[pi] * 4
