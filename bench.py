@@ -677,12 +677,22 @@ def exchange_parity(env, wl):
     diff = (fused - ref).abs().max().item()
     scale = ref.abs().max().item() + 1e-30
     bit_equal = bool(torch.equal(fused, ref))
-    ok = bit_equal if env.world == 2 else diff <= 1e-5 * scale
+    # the GEMM-pushed matrices: one f32 sum per element, a + b at two ranks is order independent -> bit equal there.  The
+    # other tensors (bias column sums, the 10-row dW of the skinny kernel) are accumulated with f32 atomics inside each
+    # backward, so two runs of the same backward already differ in the last bits: those are compared to rounding.
+    lay = wl.fused.layout
+    fused_equal = True
+    for pi in wl.fused.fused:
+        lo, n = lay.offsets[pi], int(np.prod(lay.shapes[pi]))
+        fused_equal = fused_equal and bool(torch.equal(fused[lo:lo + n], ref[lo:lo + n]))
+    ok = diff <= 1e-5 * scale and (fused_equal or env.world != 2)
     flag = torch.tensor([1 if ok else 0], device=fused.device)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    return {"ok_all_ranks": bool(int(flag.item()) == 1), "bit_equal_rank0": bit_equal, "max_abs_diff": diff,
+    return {"ok_all_ranks": bool(int(flag.item()) == 1), "bit_equal_rank0": bit_equal,
+            "gemm_pushed_matrices_bit_equal_rank0": fused_equal, "max_abs_diff": diff,
             "max_abs_ref": scale, "elements": int(ref.numel()),
-            "what": "fused NVLink exchange vs NCCL all-reduce of the locally computed gradient bucket, same inputs"}
+            "what": "fused NVLink exchange vs NCCL all-reduce of the locally computed gradient bucket, same inputs; bound: "
+                    "1e-5 * max|ref| everywhere, and at two ranks bit equality of the GEMM-pushed matrices"}
 
 
 def measured_traffic(key):

@@ -161,8 +161,11 @@ struct Gradient {
     Gradient* r = root();
     r->is_const = false;
     if (r->ptr && !r->is_zero) {
-      if (r->owned)
-        r->stale = true;  // owned memory: clear lazily (first full overwrite or first read)
+      if (r->owned || (r->rs_world > 1 && r->rs_slots[0]))
+        // owned memory: clear lazily (first full overwrite or first read).  Also a slice of a data-parallel bucket with
+        // a fused-exchange plan: the exchange rewrites the whole slice every step, so clearing 64 MB first only moves
+        // bytes; a reader through the graph still gets its zeros (get() honours `stale`)
+        r->stale = true;
       else
         ck(r->ctx, nk_memset0(r->ctx, r->ptr, size_t(r->n()) * esize(r->dtype)));  // caller-visible memory
     }

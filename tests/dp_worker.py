@@ -1,6 +1,7 @@
 """Two-or-more-GPU worker for tests/test_gpu_dp.py (launched with torchrun, one process per GPU):
-the fused data-parallel exchange (nk_gemm_rs -> nk_peer_barrier -> nk_reduce_bcast) must hand every replica the same
-gradients as computing dW locally and summing it with an NCCL all-reduce."""
+the fused data-parallel exchange (nk_gemm_rs -> nk_reduce_exchange, nk_peer_allreduce_small) must hand every replica the
+same gradients as computing dW locally and summing it with an NCCL all-reduce; then nk_allreduce_sum (the context-owned
+NCCL communicator behind the C ABI) on its own."""
 import os
 import sys
 
@@ -77,6 +78,24 @@ def main():
     ex.wait()
     stream.synchronize()
     assert ex.pushed == pushed_before
+    # ---- the plain collective behind the C ABI (nk_comm_*, nk_allreduce_sum): what a host without peer-memory set-up (or
+    # without Python) would call after backward().  Only the 128-byte id travels over the process group.
+    import ctypes as C
+    from neuronika_b200 import _lib as L
+    box = [None]
+    if rank == 0:
+        idbuf = C.create_string_buffer(128)
+        L.check(L.lib.nk_comm_unique_id(dev.ctx, idbuf), dev.ctx)
+        box[0] = bytes(idbuf.raw)
+    dist.broadcast_object_list(box, src=0)
+    L.check(L.lib.nk_comm_init_rank(dev.ctx, world, rank, C.create_string_buffer(box[0], 128)), dev.ctx)
+    assert L.lib.nk_comm_world(dev.ctx) == world and L.lib.nk_comm_rank(dev.ctx) == rank
+    n_ar = 1 << 20
+    base = np.arange(n_ar, dtype=np.float32) % 251
+    mine = dev.from_ndarray(base * (rank + 1), nk.F32)
+    L.check(L.lib.nk_allreduce_sum(dev.ctx, C.c_void_p(mine.ptr.value), n_ar, 0), dev.ctx)
+    stream.synchronize()
+    ok = ok and bool(np.array_equal(mine.as_ndarray(), base * (world * (world + 1) // 2)))   # small integers: exact in f32
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
