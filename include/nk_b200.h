@@ -68,6 +68,12 @@ uint64_t nk_launch_count(nk_ctx* ctx);
 int nk_sm_count(nk_ctx* ctx);
 int nk_gemm_config(nk_ctx* ctx, int engine /* nk_gemm_engine */);
 int nk_conv_config(nk_ctx* ctx, int engine /* nk_conv_engine */);
+/* Optional tail split of the CTA-pair GEMM: the tiles of a last, at most half full wave are cut in two k halves on two
+ * pairs each (the first half publishes its f32 accumulator rows, the second adds them in its epilogue), so that 256
+ * tiles on 74 pairs take 3.5 tile times instead of 4.  Default: OFF -- at 4096^3 the hand-over (9 MB of partial sums
+ * through L2 plus the wait) costs more than the half tile it saves (0.100 vs 0.094 ms), and the balanced grid leaves
+ * 20 SMs to kernels of another stream (the data-parallel exchange).  Kept for shapes with long k loops. */
+int nk_gemm_tail_split(nk_ctx* ctx, int enable);
 /* name of the kernel variant the last nk_gemm call used ("tcgen05_nt_128x256", "simt", ...) */
 const char* nk_last_gemm_kernel(nk_ctx* ctx);
 

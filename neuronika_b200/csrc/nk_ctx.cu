@@ -143,6 +143,7 @@ int nk_ctx_destroy(nk_ctx* ctx) {
     nk_graph_destroy(ctx, g);
   }
   if (ctx->workspace) cudaFree(ctx->workspace);
+  if (ctx->gemm_split_mem) cudaFree(ctx->gemm_split_mem);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -176,6 +177,11 @@ int nk_gemm_config(nk_ctx* ctx, int engine) {
   if (!ctx) return NK_ERR_INVALID_ARG;
   NK_REQUIRE(ctx, engine >= NK_GEMM_AUTO && engine <= NK_GEMM_TCGEN05, "nk_gemm_config: bad engine %d", engine);
   ctx->gemm_engine = engine;
+  return NK_OK;
+}
+int nk_gemm_tail_split(nk_ctx* ctx, int enable) {
+  if (!ctx) return NK_ERR_INVALID_ARG;
+  ctx->gemm_tail_split = enable != 0;
   return NK_OK;
 }
 int nk_conv_config(nk_ctx* ctx, int engine) {

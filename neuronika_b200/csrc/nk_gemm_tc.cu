@@ -63,7 +63,36 @@ struct GemmParams {
   // no reduce-scatter, not batched, and C is TMA-addressable.
   int tma_store;
   int cta_pairs;   // host-side: launch the cta_group::2 variant (the B tensor map then has 128-row boxes)
+  // tail split (CTA pairs only): the tiles of the last, partial wave are cut in two k halves, each half on its own
+  // pair.  The first half writes its raw f32 accumulator rows to `split_ws` and raises a per-warp flag; the second half
+  // adds them to its own in the epilogue.  full_waves whole waves of tiles come first; split_tiles = 0: off.
+  int split_tiles, full_waves, allow_split;
+  float* split_ws;
+  uint32_t* split_flags;
 };
+
+// one unit of work of a persistent CTA (pair): a whole tile, or one k half of a tile of the split tail
+struct Work {
+  int tile, kb0, kb1, kind, split_index;   // kind 0 = whole tile, 1 = first half (publishes), 2 = second half (adds + stores)
+};
+__device__ __forceinline__ bool get_work(const GemmParams& p, int it, int unit, int units, int num_tiles, int kblocks, Work& w) {
+  w.kb0 = 0, w.kb1 = kblocks, w.kind = 0, w.split_index = 0;
+  if (p.split_tiles == 0) {
+    w.tile = unit + it * units;
+    return w.tile < num_tiles;
+  }
+  if (it < p.full_waves) {
+    w.tile = unit + it * units;
+    return true;
+  }
+  if (it > p.full_waves || unit >= 2 * p.split_tiles) return false;
+  w.split_index = unit >> 1;
+  w.tile = p.full_waves * units + w.split_index;
+  const int half = kblocks / 2;
+  if (unit & 1) w.kb0 = half, w.kind = 2;
+  else w.kb1 = half, w.kind = 1;
+  return true;
+}
 
 __device__ __forceinline__ int tile_m_block(const GemmParams& p, int tile) {
   const int t = tile % p.num_m_blocks;
@@ -293,13 +322,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = int(blockIdx.x) / CG; tile < num_tiles; tile += int(gridDim.x) / CG) {
+      Work wk;
+      for (int it = 0; get_work(p, it, int(blockIdx.x) / CG, int(gridDim.x) / CG, num_tiles, p.num_k_blocks, wk); ++it) {
+        const int tile = wk.tile;
         int m_blk, n_blk, b0 = 0, b1 = 1;
         tile_coords(p, BATCH ? tile % tiles_mn : tile, m_blk, n_blk);
         if (BATCH) batch_range(tile / tiles_mn, b0, b1);
         const int m0 = (m_blk * CG + int(cta_rank)) * BLOCK_M, n0 = n_blk * BLOCK_N + int(cta_rank) * LOAD_N;
         for (int bb = b0; bb < b1; ++bb)
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           if constexpr (CG == 2) {
             // both CTAs' loads complete on the leader's barrier, which expects the bytes of both
@@ -361,11 +392,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = int(blockIdx.x) / CG; tile < num_tiles; tile += int(gridDim.x) / CG) {
+      Work wk;
+      for (int it = 0; get_work(p, it, int(blockIdx.x) / CG, int(gridDim.x) / CG, num_tiles, p.num_k_blocks, wk); ++it) {
+        const int tile = wk.tile;
         ptx::mbar_wait(tmem_empty_bar(as), aphase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(as * BLOCK_N);
-        int k_total = p.num_k_blocks;
+        int k_total = wk.kb1 - wk.kb0;
         if (BATCH) {
           int b0, b1;
           batch_range(tile / tiles_mn, b0, b1);
@@ -413,7 +446,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t store_buf = 0;                      // which of this warp's two store tiles the next chunk uses
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = int(blockIdx.x) / CG; tile < num_tiles; tile += int(gridDim.x) / CG) {
+    Work wk;
+    for (int it = 0; get_work(p, it, int(blockIdx.x) / CG, int(gridDim.x) / CG, num_tiles, p.num_k_blocks, wk); ++it) {
+      const int tile = wk.tile;
       int m_blk, n_blk;
       tile_coords(p, BATCH ? tile % tiles_mn : tile, m_blk, n_blk);
       const int64_t c_off = (BATCH && !p.batch_reduce) ? int64_t(tile / tiles_mn) * p.c_batch_stride : 0;
@@ -423,6 +458,80 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::mbar_wait(tmem_full_bar(as), aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BLOCK_N);
+      // ---- split tail: this warp's 32 rows of the other k half's accumulator live at `part` as [chunk][lane][32 floats]
+      const float4* part = nullptr;
+      uint32_t* split_flag = nullptr;
+      if constexpr (CG == 2 && !BATCH) {
+        if (wk.kind != 0) {
+          const size_t wi = (size_t(wk.split_index) * 2 + cta_rank) * 4 + q;
+          float4* mine = reinterpret_cast<float4*>(p.split_ws + wi * (size_t(BLOCK_N) * 32));
+          split_flag = p.split_flags + wi;
+          if (wk.kind == 1) {
+            // first k half: publish the raw accumulator rows (a warp writes 4 KB contiguous per chunk), raise the flag
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+              ptx::tmem_ld_wait();
+              float4* dst = mine + (size_t(c) * 32 + lane) * 8;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                     __uint_as_float(r[4 * j + 3]));
+            }
+            __threadfence();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::mbar_arrive_leader(tmem_empty_bar(as));
+              asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(split_flag), "r"(1u) : "memory");
+            }
+            as ^= 1;
+            if (as == 0) aphase ^= 1u;
+            continue;
+          }
+          // second k half: wait for the first one's rows (its pair runs concurrently and waits for nobody)
+          if (lane == 0) {
+            const long long t0 = clock64();
+            for (;;) {
+              uint32_t v;
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(split_flag) : "memory");
+              if (v != 0u) break;
+              if (clock64() - t0 > (1ll << 32)) {
+                printf("nk_b200: gemm split-tail watchdog: block %d warp %d tile %d\n", blockIdx.x, warp_idx, wk.tile);
+                __trap();
+              }
+              __nanosleep(64);
+            }
+          }
+          __syncwarp();
+          part = mine;
+        }
+      }
+      // adds the other half's partial sums of 32-column chunk c32 to the freshly loaded accumulator values
+      auto add_partial = [&](uint32_t* r, int c32) {
+        if constexpr (CG == 2 && !BATCH) {
+          if (part) {
+            const float4* src = part + (size_t(c32) * 32 + lane) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 v = __ldcg(src + j);   // written by another SM: read through L2
+              r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + v.x);
+              r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + v.y);
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + v.z);
+              r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
+            }
+          }
+        }
+      };
+      auto split_done = [&]() {   // the partial rows have been consumed: the flag is zero again for the next launch
+        if constexpr (CG == 2 && !BATCH) {
+          if (part) {
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(split_flag) = 0u;
+          }
+        }
+      };
       if constexpr (BLOCK_N >= 64 && !BATCH) {
         if (p.tma_store) {
           // ---- staged epilogue: 32 rows x 128 bytes per tile (32 f32 / 64 bf16 columns), written 128B-swizzled so that
@@ -442,6 +551,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               uint32_t r[32];
               ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
               ptx::tmem_ld_wait();
+              add_partial(r, c);
               float v[32];
               scale_and_bias(p, row, col0, r, col0 + 32 <= p.N, v);
 #pragma unroll
@@ -457,6 +567,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 uint32_t r[32];
                 ptx::tmem_ld_32x32b_x32(taddr + c * 64 + hc * 32, r);
                 ptx::tmem_ld_wait();
+                add_partial(r, c * 2 + hc);
                 float v[32];
                 scale_and_bias(p, row, col0 + hc * 32, r, col0 + hc * 32 + 32 <= p.N, v);
 #pragma unroll
@@ -482,6 +593,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
             store_buf ^= 1u;
           }
+          split_done();
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -501,6 +613,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
           ptx::tmem_ld_wait();
+          add_partial(r, c);
           const int64_t col0 = int64_t(n_blk) * BLOCK_N + c * 32;
           if constexpr (sizeof(TC) == 4 && BLOCK_N == 256) {
             if (p.rs_world) {
@@ -540,6 +653,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int64_t col0 = int64_t(n_blk) * BLOCK_N;
         if (row < p.M && col0 < p.N) epilogue_store_chunk32<TC>(p, row, col0, r, 16, false, c_off, atomic);
       }
+      split_done();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -640,6 +754,30 @@ int launch_cfg(nk_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, GemmPa
   const int units = ctx->sm_count / CG;                       // CTAs, or CTA pairs
   const int waves = (num_tiles + units - 1) / units;
   int grid = ((num_tiles + waves - 1) / waves) * CG;
+  p.split_tiles = 0, p.full_waves = 0, p.split_ws = nullptr, p.split_flags = nullptr;
+  if (CG == 2 && !BATCH && p.rs_world == 0 && p.allow_split) {
+    // tail split: when the last wave is at most half full, its tiles are cut in two k halves on two pairs each -- 256
+    // tiles on 74 pairs then take 3.5 tile times instead of 4
+    const int full = num_tiles / units, rem = num_tiles - full * units;
+    constexpr size_t kFlagBytes = 4096;                                       // 2 x 4 words per split tile, <= 74 tiles
+    const size_t ws_bytes = size_t(units / 2) * 2 * 4 * (size_t(BLOCK_N) * 32) * sizeof(float);
+    if (rem > 0 && 2 * rem <= units && p.num_k_blocks >= 8) {
+      if (!ctx->gemm_split_mem && !ctx->capturing) {
+        if (cudaMalloc(&ctx->gemm_split_mem, kFlagBytes + ws_bytes) == cudaSuccess) {
+          cudaMemsetAsync(ctx->gemm_split_mem, 0, kFlagBytes, ctx->stream);
+        } else {
+          (void)cudaGetLastError();
+          ctx->gemm_split_mem = nullptr;
+        }
+      }
+      if (ctx->gemm_split_mem) {
+        p.split_tiles = rem, p.full_waves = full;
+        p.split_flags = static_cast<uint32_t*>(ctx->gemm_split_mem);
+        p.split_ws = reinterpret_cast<float*>(static_cast<char*>(ctx->gemm_split_mem) + kFlagBytes);
+        grid = units * CG;
+      }
+    }
+  }
   size_t smem = C_::SMEM_BYTES;
   if (p.rs_world) {
     if (BLOCK_N != 256 || sizeof(TC) != 4 || p.N % 4 != 0)
@@ -725,10 +863,11 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   }
   // development knobs (tile sweeps, descriptor sweeps on hardware): the environment is read ONCE per process
   struct Knobs {
-    uint32_t block_n, a_lbo, a_sbo, b_lbo, b_sbo, direct_store, single_cta;
+    uint32_t block_n, a_lbo, a_sbo, b_lbo, b_sbo, direct_store, single_cta, no_split;
     Knobs() : block_n(env_u32("NK_GEMM_BLOCK_N", 0)), a_lbo(env_u32("NK_DESC_A_LBO", 0)), a_sbo(env_u32("NK_DESC_A_SBO", 0)),
               b_lbo(env_u32("NK_DESC_B_LBO", 0)), b_sbo(env_u32("NK_DESC_B_SBO", 0)),
-              direct_store(env_u32("NK_GEMM_DIRECT_STORE", 0)), single_cta(env_u32("NK_GEMM_SINGLE_CTA", 0)) {}
+              direct_store(env_u32("NK_GEMM_DIRECT_STORE", 0)), single_cta(env_u32("NK_GEMM_SINGLE_CTA", 0)),
+              no_split(env_u32("NK_GEMM_NO_SPLIT", 0)) {}
   };
   static const Knobs knobs;
   if (knobs.block_n) block_n = int(knobs.block_n);
@@ -780,6 +919,7 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   // when the 256 rows of a pair belong to one owner); narrow outputs stay on single CTAs
   p.cta_pairs = (block_n == 256 && M > BLOCK_M && (ctx->sm_count % 2) == 0 && knobs.single_cta == 0 &&
                  (p.rs_world == 0 || M % (int64_t(p.rs_world) * 2 * BLOCK_M) == 0)) ? 1 : 0;   // a pair's 256 rows: one owner
+  p.allow_split = knobs.no_split == 0 && ctx->gemm_tail_split;
   CUtensorMap ta, tb;
   int rc;
   if (a_mn)
@@ -860,7 +1000,8 @@ int nk_gemm_tcgen05_batched(nk_ctx* ctx, int transA, int transB, int64_t M, int6
   p.num_k_blocks = int((K + BLOCK_K - 1) / BLOCK_K);
   p.rs_world = 0, p.m_rot = 0, p.rs_rows = M;
   for (int i = 0; i < 8; ++i) p.rs_dst[i] = nullptr;
-  p.tma_store = 0, p.cta_pairs = 0;
+  p.tma_store = 0, p.cta_pairs = 0, p.allow_split = 0, p.split_tiles = 0, p.full_waves = 0, p.split_ws = nullptr,
+  p.split_flags = nullptr;
   p.batch = int(batch), p.a_batched = strideA != 0, p.b_batched = strideB != 0, p.batch_reduce = reduce ? 1 : 0, p.splits = 1;
   p.c_batch_stride = strideC;
   p.a_lbo = a_mn ? BLOCK_K * 128 : 16, p.a_sbo = 1024, p.a_kstep = a_mn ? UMMA_K * 128 : UMMA_K * 2;

@@ -34,6 +34,10 @@ struct nk_ctx {
   size_t workspace_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int gemm_engine = NK_GEMM_AUTO;
+  // tail split of the CTA-pair GEMM (nk_gemm_tc.cu): flags (zero between launches) followed by the f32 partial
+  // accumulators of the first k halves; allocated once, outside any capture
+  void* gemm_split_mem = nullptr;
+  bool gemm_tail_split = false;   // measured slower than the balanced grid at 4096^3 (profiles/r02_gemm_pairs_probe.txt)
   int conv_engine = NK_CONV_AUTO;
   const char* last_gemm_kernel = "none";
   const char* last_conv_kernel = "none";

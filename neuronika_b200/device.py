@@ -59,6 +59,10 @@ class Device:
     def gemm_engine(self, engine: str) -> None:
         L.check(L.lib.nk_gemm_config(self.ctx, {"auto": 0, "simt": 1, "tcgen05": 2}[engine]), self.ctx)
 
+    def gemm_tail_split(self, enable: bool) -> None:
+        """False: the CTA-pair GEMM keeps its balanced grid (SMs left free for kernels of another stream)"""
+        L.check(L.lib.nk_gemm_tail_split(self.ctx, 1 if enable else 0), self.ctx)
+
     def conv_engine(self, engine: str) -> None:
         """"auto": tensor-core kernels wherever they apply; "direct": CUDA-core kernels only; "unfused": auto without the
         one-pass dX + dW backward kernel"""

@@ -324,6 +324,8 @@ class FusedGradientExchange:
         # the side stream gets its own context handle bound to the same device: kernels are enqueued on self.comm
         if self.comm_device is None:
             self.comm_device = Device(self.device.index, stream=self.comm.cuda_stream)
+        # the exchange kernels run beside the dX GEMMs: keep the GEMM's balanced grid (20 SMs free), never the tail split
+        self.device.gemm_tail_split(False)
         self._params = list(params)
         lay = self.layout
         for pi, p in enumerate(params):
