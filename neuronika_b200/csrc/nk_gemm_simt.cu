@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256, 2) gemm_small_k_kernel(const TAB* __restr
 // the packed two-lane form.  The eight warps' partial sums meet in a three-round tree through shared memory (shared
 // f32 atomicAdd is a compare-and-swap loop in SASS, ATOMS.CAST.SPIN: 8-way contended it cost more than the loop), and
 // one warp ends the block with M x 128 global reductions.
-constexpr int kSmChunk = 256;   // rows of A staged per pass
+constexpr int kSmChunk = 512;   // rows of A staged per pass (a whole k slab of the usual launch)
 template <typename TAB, int MP>
 __global__ void __launch_bounds__(256) gemm_small_m_kernel(const TAB* __restrict__ A, const TAB* __restrict__ B,
                                                            float* __restrict__ scratch, int M, int64_t N, int64_t K,
@@ -375,17 +375,24 @@ __global__ void __launch_bounds__(256) gemm_small_m_kernel(const TAB* __restrict
     }
     __syncthreads();
     if (valid) {
-      for (int kb = warp; kb < rows; kb += 64) {      // 8 rows of this warp per pass: kb, kb + 8, ..., kb + 56
-        float bv[8][4];
+      // software pipeline: the 8 loads of the NEXT pass are issued before the FMAs of the current one, so a warp always has
+      // loads in flight (kept raw, converted at use: 16 registers per set)
+      Raw4<TAB> cur[8], nxt[8];
+      auto fetch = [&](Raw4<TAB>* dst, int kb) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          if (kb + 8 * u < rows) load4<TAB>(B + (k0 + kb + 8 * u) * ldb + n, vb, valid, bv[u]);
-          else bv[u][0] = bv[u][1] = bv[u][2] = bv[u][3] = 0.f;
+          if (kb + 8 * u < rows) dst[u] = load_raw4<TAB>(B + (k0 + kb + 8 * u) * ldb + n, vb, valid);
+          else dst[u] = Raw4<TAB>{};
         }
+      };
+      fetch(cur, warp);
+      for (int kb = warp; kb < rows; kb += 64) {      // 8 rows of this warp per pass: kb, kb + 8, ..., kb + 56
+        if (kb + 64 < rows) fetch(nxt, kb + 64);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int r = kb + 8 * u < rows ? kb + 8 * u : 0;   // (bv is zero beyond the slab)
-          const float2 b01 = make_float2(bv[u][0], bv[u][1]), b23 = make_float2(bv[u][2], bv[u][3]);
+          const int r = kb + 8 * u < rows ? kb + 8 * u : 0;   // (the operand is zero beyond the slab)
+          const float2 b01 = make_float2(raw_get<TAB>(cur[u], 0), raw_get<TAB>(cur[u], 1));
+          const float2 b23 = make_float2(raw_get<TAB>(cur[u], 2), raw_get<TAB>(cur[u], 3));
 #pragma unroll
           for (int m4 = 0; m4 < MP / 4; ++m4) {
             const float4 a4 = *reinterpret_cast<const float4*>(&As[r][m4 * 4]);
@@ -398,6 +405,8 @@ __global__ void __launch_bounds__(256) gemm_small_m_kernel(const TAB* __restrict
             }
           }
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
       }
     }
   }

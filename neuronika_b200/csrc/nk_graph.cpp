@@ -127,7 +127,10 @@ struct Gradient {
       fail(NK_ERR_INVALID_ARG,
            "Trying to get a de-allocated gradient. Switch on the gradients first by using `.with_grad()`");
     if (!r->ptr) {
-      ck(r->ctx, nk_alloc(r->ctx, size_t(r->n()) * esize(r->dtype), &r->ptr));
+      if (r->is_const)   // a deferred fill writes every element right below: the zero fill of nk_alloc would only move bytes
+        ck(r->ctx, nk_alloc_uninit(r->ctx, size_t(r->n()) * esize(r->dtype), &r->ptr));
+      else
+        ck(r->ctx, nk_alloc(r->ctx, size_t(r->n()) * esize(r->dtype), &r->ptr));
       r->is_zero = true;
       r->stale = false;
     }
@@ -137,6 +140,7 @@ struct Gradient {
     }
     if (r->is_const) {  // a reader wants the bytes of a deferred fill
       r->is_const = false;
+      r->is_zero = false;
       ck(r->ctx, nk_fill(r->ctx, r->ptr, r->dtype, size_t(r->n()), r->const_val));
     }
     return r->ptr;
