@@ -158,7 +158,9 @@ def test_config4_mlp_step_full_size_matches_oracle(nk, dev, O):
         assert fro <= 1e-2, (i, fro)
         assert outl <= 1e-4, (i, outl, float(err.max()), rms)
         assert float(err.max()) <= rms, (i, float(err.max()), rms)
-        assert abs(float(g.astype(np.float64).sum()) - float(want.astype(np.float64).sum())) <= 2e-2 * rms * np.sqrt(g.size) + 1e-6, i
+        # checksum of the whole tensor: the two sums agree to 0.2 % of the tensor's L1 norm
+        assert abs(float(g.astype(np.float64).sum()) - float(want.astype(np.float64).sum())) <= \
+            2e-3 * float(np.abs(want.astype(np.float64)).sum()) + 1e-6, i
     for i, (wnew, (w0, g)) in enumerate(zip(got_w, [(v, want_grads[j]) for j, v in enumerate([a for pair in init for a in pair])])):
         want_w = O.bf16_round(w0 - F32(0.01) * g)
         assert np.all(np.abs(wnew - want_w) <= 2.0 ** -7 * np.abs(want_w) + 1e-6), i
