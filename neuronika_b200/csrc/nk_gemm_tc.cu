@@ -8,12 +8,14 @@
 // A "transposed" operand is never copied: TMA loads it as stored and the UMMA shared-memory
 // descriptor is MN-major instead of K-major.
 //
-// Structure (one CTA per SM, persistent over output tiles):
+// Structure (persistent over output tiles; one CTA per SM, or -- for outputs wider and taller than 128 -- one CTA PAIR per
+// TPC running cta_group::2 UMMAs of M = 256, see the comment on gemm_tc_kernel):
 //   warp 0      : TMA producer  -- cp.async.bulk.tensor 128B-swizzled boxes into a kStages smem ring
-//   warp 1      : tcgen05.mma issuer (one lane) + TMEM allocation; accumulators 128 x BLOCK_N f32,
-//                 double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1
-//   warps 2..5  : epilogue -- tcgen05.ld (32 lanes x 32 columns per warp), alpha/beta/bias/ReLU in
-//                 registers, 16-byte global stores
+//   warp 1      : tcgen05.mma issuer (one lane; in a pair: the even CTA's) + TMEM allocation; accumulators
+//                 128 x BLOCK_N f32 per CTA, double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2..5  : epilogue -- tcgen05.ld (32 lanes x 32 columns per warp), alpha/bias/ReLU in registers, then either
+//                 128B-swizzled staging tiles in shared memory + TMA bulk stores (plain outputs), or direct 16-byte
+//                 global stores (beta != 0, ReLU-backward mask, reduce-scatter over NVLink, batched launches)
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue).
 #include <stdlib.h>
 

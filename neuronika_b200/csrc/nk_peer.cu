@@ -6,10 +6,14 @@
 //   1. reduce-scatter inside the GEMM epilogue: nk_gemm_rs runs the tcgen05 dW GEMM, and the epilogue stores row shard
 //      o of the local product straight into rank o's slot buffer over NVLink (slot index = this rank) -- the transfer
 //      overlaps the MMAs tile by tile and the local gradient is never written to local HBM;
-//   2. nk_peer_barrier: flag exchange through peer memory (all pushes landed);
-//   3. nk_reduce_bcast: the owner sums its `world` slots in rank order (so every replica receives bit-identical sums)
-//      and stores the result into EVERY replica's gradient buffer over NVLink (the all-gather half);
-//   4. nk_peer_barrier again, then the ordinary nk_sgd_step on every replica.
+//   2. nk_reduce_exchange: ONE kernel for "all pushes landed" (flag exchange through peer memory) -> the owner sums its
+//      `world` slots in rank order (so every replica receives bit-identical sums) and stores the result into EVERY
+//      replica's gradient buffer over NVLink (the all-gather half) -> "all sums landed"; device-resident epoch, so the
+//      launch is the same every step and can live in a CUDA graph (the r01 three-launch form -- nk_peer_barrier,
+//      nk_reduce_bcast, nk_peer_barrier -- is kept);
+//   3. nk_peer_allreduce_small: biases and other small tensors, one single-CTA kernel through peer memory, issued the
+//      moment the gradient is final;
+//   4. then the ordinary nk_sgd_step on every replica.
 // Memory that peers touch comes from nk_ipc_alloc (plain cudaMalloc: CUDA IPC cannot export pool memory) and is
 // mapped into the other processes with nk_ipc_export / nk_ipc_open.
 #include "nk_internal.cuh"
