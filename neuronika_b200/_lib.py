@@ -82,6 +82,7 @@ _PROTOS = {
     "nk_gemm_bias_act": (i32, [vp, i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, i32, i32,
                                vp, i32, i32]),
     "nk_gemm_relu_bwd": (i32, [vp, i32, i32, i64, i64, i64, vp, i64, vp, i64, f32, vp, i64, i32, i32, vp]),
+    "nk_gemm_relu_bwd_colsum": (i32, [vp, i32, i32, i64, i64, i64, vp, i64, vp, i64, f32, vp, i64, i32, i32, vp, vp]),
     "nk_add_bcast_fwd": (i32, [vp, vp, vp, vp, i32, i32, pi64, i32, pi64, i32, pi64]),
     "nk_unbroadcast_acc": (i32, [vp, vp, i32, i32, pi64, vp, i32, i32, pi64, f32]),
     "nk_relu_fwd": (i32, [vp, vp, vp, sz, i32]),

@@ -19,6 +19,8 @@ struct Epilogue {
   int relu;
   const void* mask = nullptr;   // small-K kernel only: (M, N) tensor of C's type and pitch; v = mask > 0 ? v : 0 before the
                                 // beta accumulate (the ReLU backward of the layer below, relu/mod.rs:71-78)
+  float* colsum = nullptr;      // small-K kernel only: N floats, += column sums of the stored values (the bias gradient of
+                                // the layer below), f32 atomics; beta must be 0
 };
 
 template <typename TC>
@@ -300,6 +302,7 @@ __global__ void __launch_bounds__(256, 2) gemm_small_k_kernel(const TAB* __restr
                                : static_cast<const float*>(ep.bias)[n + j];
   }
   const int rows = int(M - m0 < kRows ? M - m0 : kRows);
+  float csum[4] = {0.f, 0.f, 0.f, 0.f};
   for (int r0 = 0; r0 < rows; r0 += kFlight) {
     Raw4<TC> old[kFlight], msk[kFlight];
     if (ep.beta != 0.f) {
@@ -336,9 +339,15 @@ __global__ void __launch_bounds__(256, 2) gemm_small_k_kernel(const TAB* __restr
         v += bias[j];
         if (ep.relu) v = v > 0.f ? v : 0.f;
         acc[j] = v;
+        csum[j] += nk_to_f32<TC>(nk_from_f32<TC>(v));   // what the output tensor will hold
       }
       store4<TC>(C + (m0 + r0 + rr) * ldc + n, vc, valid, acc);
     }
+  }
+  if (ep.colsum) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < valid) atomicAdd(ep.colsum + n + j, csum[j]);
   }
 }
 
@@ -501,9 +510,10 @@ int launch_skinny(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int
 // C = mask > 0 ? A.B : 0  (+ beta*C) for the skinny NN shape only (K <= 16): the dX product of a 10-wide layer with the ReLU
 // backward of the layer below applied on the way out.  NK_ERR_UNSUPPORTED (nothing done) for every other shape.
 int nk_gemm_simt_small_k_masked(nk_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
-                                int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype, const void* mask) {
-  if (K > kSkinnyMax || K <= 0 || N < 256 || (M + 63) / 64 > 65535) return NK_ERR_UNSUPPORTED;
-  Epilogue ep{1.f, beta, nullptr, 0, 0, mask};
+                                int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype, const void* mask,
+                                float* colsum) {
+  if (K > kSkinnyMax || K <= 0 || N < 256 || (M + 63) / 64 > 65535 || (colsum && beta != 0.f)) return NK_ERR_UNSUPPORTED;
+  Epilogue ep{1.f, beta, nullptr, 0, 0, mask, colsum};
   bool handled = false;
   int rc;
   if (ab_dtype == NK_F32 && c_dtype == NK_F32)

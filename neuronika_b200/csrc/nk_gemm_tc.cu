@@ -45,6 +45,9 @@ struct GemmParams {
   int relu;
   const void* mask;    // optional (M, N) tensor of C's element type and leading dimension: v = mask > 0 ? v : 0 before the
                        // beta accumulate -- the ReLU backward of the layer below fused into the dX GEMM (relu/mod.rs:71-78)
+  float* colsum;       // optional (N floats, accumulated with atomics; beta must be 0): column sums of the values the
+                       // epilogue stores -- the bias gradient of the layer below (un-broadcast of its Addition,
+                       // addition/mod.rs:81-135) without a separate pass over the (M, N) gradient
   int num_m_blocks, num_n_blocks, num_k_blocks;
   // UMMA descriptor parameters (bytes)
   uint32_t a_lbo, a_sbo, a_kstep;
@@ -178,6 +181,38 @@ __device__ __forceinline__ void scale_and_bias(const GemmParams& p, int64_t row,
                               : static_cast<const float*>(p.bias)[col0 + j];
     }
   }
+}
+
+// column sums of one 32-row x 32-column chunk (all 32 lanes of the warp take part; lane = row): the values are exactly the
+// ones epilogue_store_chunk32 stores (alpha, mask, rounding to the output type), rows / columns outside the matrix count as
+// zero.  A butterfly of 31 shuffles leaves the sum of column j on lane j; one atomic per column and chunk.
+template <typename TC>
+__device__ __forceinline__ void epilogue_colsum_chunk32(const GemmParams& p, int64_t row, int64_t col0, const uint32_t* r,
+                                                        int lane) {
+  float v[32];
+  const bool live = row < p.M;
+  const TC* mrow = (p.mask && live) ? static_cast<const TC*>(p.mask) + row * p.ldc + col0 : nullptr;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = 0.f;
+    if (live && col0 + j < p.N) {
+      x = p.alpha * __uint_as_float(r[j]);
+      if (mrow) x = nk_to_f32<TC>(mrow[j]) > 0.f ? x : 0.f;
+      x = nk_to_f32<TC>(nk_from_f32<TC>(x));   // what the output tensor will hold
+    }
+    v[j] = x;
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  if (col0 + lane < p.N) atomicAdd(p.colsum + col0 + lane, v[0]);
 }
 
 template <typename TC>
@@ -643,6 +678,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               continue;
             }
           }
+          if (p.colsum && col0 < p.N) epilogue_colsum_chunk32<TC>(p, row, col0, r, lane);
           if (row < p.M && col0 < p.N) epilogue_store_chunk32<TC>(p, row, col0, r, 32, vec_ok, c_off, atomic);
         }
       } else {
@@ -843,8 +879,9 @@ bool nk_gemm_tcgen05_supported(int transA, int transB, int64_t M, int64_t N, int
 
 int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,
                     int64_t lda, const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int c_dtype,
-                    const void* bias, int bias_dtype, int relu, const void* mask) {
+                    const void* bias, int bias_dtype, int relu, const void* mask, float* colsum) {
   if (!nk_gemm_tcgen05_supported(transA, transB, M, N, K, A, lda, B, ldb)) return NK_ERR_UNSUPPORTED;
+  if (colsum && (N <= 16 || beta != 0.f)) return NK_ERR_UNSUPPORTED;   // (the narrow-tile epilogue has no column-sum path)
   const bool a_mn = transA != 0;   // op(A) = A^T  -> A stored (K, M), M contiguous
   const bool b_mn = transB == 0;   // op(B) = B    -> B stored (K, N), N contiguous
   // tile width: widest that does not leave most of a tile empty
@@ -887,6 +924,7 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   p.bias_per_row = 0;
   p.relu = relu;
   p.mask = mask;
+  p.colsum = colsum;
   p.batch = 1, p.a_batched = p.b_batched = p.batch_reduce = 0, p.splits = 1, p.c_batch_stride = 0;
   p.num_m_blocks = int((M + BLOCK_M - 1) / BLOCK_M);
   p.num_n_blocks = 0;
@@ -948,7 +986,7 @@ int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, i
   // staged TMA-store epilogue wherever the output is plain (no accumulate, mask or reduce-scatter) and TMA-addressable
   CUtensorMap tc;
   p.tma_store = 0;
-  if (beta == 0.f && !mask && p.rs_world == 0 && block_n >= 64 && knobs.direct_store == 0 &&
+  if (beta == 0.f && !mask && !colsum && p.rs_world == 0 && block_n >= 64 && knobs.direct_store == 0 &&
       (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * int64_t(nk_dtype_size(c_dtype))) % 16 == 0) {
     if (make_tmap_c(ctx, &tc, C, M, N, ldc, c_dtype) == NK_OK) p.tma_store = 1;
   }
@@ -996,7 +1034,7 @@ int nk_gemm_tcgen05_batched(nk_ctx* ctx, int transA, int transB, int64_t M, int6
   GemmParams p;
   p.M = M, p.N = N, p.K = K, p.ldc = ldc, p.C = C;
   p.bias = row_bias, p.bias_bf16 = bias_dtype == NK_BF16, p.bias_per_row = 1;
-  p.alpha = alpha, p.beta = 0.f, p.relu = relu, p.mask = nullptr;
+  p.alpha = alpha, p.beta = 0.f, p.relu = relu, p.mask = nullptr, p.colsum = nullptr;
   p.num_m_blocks = int((M + BLOCK_M - 1) / BLOCK_M);
   p.num_n_blocks = 0;
   p.num_k_blocks = int((K + BLOCK_K - 1) / BLOCK_K);
@@ -1052,7 +1090,7 @@ int nk_gemm_bias_act(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, 
   const bool want_tc = ab_dtype == NK_BF16 && ctx->gemm_engine != NK_GEMM_SIMT && K > 0;
   if (want_tc) {
     int rc = nk_gemm_tcgen05(ctx, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, c_dtype, bias,
-                             bias_dtype, relu, nullptr);
+                             bias_dtype, relu, nullptr, nullptr);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
     if (ctx->gemm_engine == NK_GEMM_TCGEN05)
       return nk_set_error(ctx, NK_ERR_UNSUPPORTED,
@@ -1065,25 +1103,27 @@ int nk_gemm_bias_act(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, 
                       bias_dtype, relu);
 }
 
-int nk_gemm_relu_bwd(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
-                     const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype,
-                     const void* relu_operand) {
+int nk_gemm_relu_bwd_colsum(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                            const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype,
+                            const void* relu_operand, float* colsum) {
   if (!ctx) return NK_ERR_INVALID_ARG;
   NK_REQUIRE(ctx, nk_dtype_ok(ab_dtype) && nk_dtype_ok(c_dtype), "nk_gemm_relu_bwd: bad dtype");
   NK_REQUIRE(ctx, M >= 0 && N >= 0 && K > 0, "nk_gemm_relu_bwd: bad dimension");
   if (M == 0 || N == 0) return NK_OK;
   NK_REQUIRE(ctx, A && B && C && relu_operand, "nk_gemm_relu_bwd: NULL pointer");
   NK_REQUIRE(ctx, lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "nk_gemm_relu_bwd: leading dimension too small");
+  NK_REQUIRE(ctx, !colsum || beta == 0.f, "nk_gemm_relu_bwd_colsum: the column sums are those of the product (beta must be 0)");
   if (ab_dtype == NK_BF16 && ctx->gemm_engine != NK_GEMM_SIMT) {
     int rc = nk_gemm_tcgen05(ctx, transA, transB, M, N, K, 1.f, A, lda, B, ldb, beta, C, ldc, c_dtype, nullptr, NK_F32, 0,
-                             relu_operand);
+                             relu_operand, colsum);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }
-  // the skinny NN shape (K <= 16: the layer above is 10 wide) masks in its own epilogue
+  // the skinny NN shape (K <= 16: the layer above is 10 wide) masks (and sums) in its own epilogue
   if (!transA && !transB) {
-    int rc = nk_gemm_simt_small_k_masked(ctx, M, N, K, A, lda, B, ldb, beta, C, ldc, ab_dtype, c_dtype, relu_operand);
+    int rc = nk_gemm_simt_small_k_masked(ctx, M, N, K, A, lda, B, ldb, beta, C, ldc, ab_dtype, c_dtype, relu_operand, colsum);
     if (rc != NK_ERR_UNSUPPORTED) return rc;
   }
+  if (colsum) return NK_ERR_UNSUPPORTED;   // nothing done: the caller sums the columns itself after the plain call
   // operands the tensor-core engine cannot take: the product into a temporary, then the ordinary ReLU backward
   void* tmp = nullptr;
   int rc = nk_alloc_uninit(ctx, size_t(M) * size_t(N) * nk_dtype_size(c_dtype), &tmp);
@@ -1098,6 +1138,13 @@ int nk_gemm_relu_bwd(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, 
   }
   nk_free(ctx, tmp);
   return rc;
+}
+
+int nk_gemm_relu_bwd(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                     const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype,
+                     const void* relu_operand) {
+  return nk_gemm_relu_bwd_colsum(ctx, transA, transB, M, N, K, A, lda, B, ldb, beta, C, ldc, ab_dtype, c_dtype, relu_operand,
+                                 nullptr);
 }
 
 int nk_gemm(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha, const void* A,

@@ -305,12 +305,16 @@ struct MatMulBackward : Backward {
   // masked product goes straight into the ReLU operand's gradient (nk_gemm_relu_bwd), left_grad is never materialised
   TensorP left_mask;
   GradientP left_dst;
+  // ... and the bias gradient of the layer below (the un-broadcast of its Addition's (K) row bias) is summed in the
+  // same epilogue (nk_gemm_relu_bwd_colsum): the AdditionBackward then skips its right operand
+  GradientP left_colsum;
   const char* name() const override { return t ? "MatrixMatrixMulTBackward" : "MatrixMatrixMulBackward"; }
   void targets(std::vector<Gradient*>& out) override {
     if (left_dst)
       out.push_back(left_dst->root());
     else if (left_grad)
       out.push_back(left_grad->root());
+    if (left_dst && left_colsum) out.push_back(left_colsum->root());
     if (right_grad) out.push_back(right_grad->root());
   }
   void backward() override {
@@ -363,9 +367,32 @@ struct MatMulBackward : Backward {
     if (left_dst) {  // (M,K), ReLU backward of the layer below in the epilogue: dZ += (Y > 0) * (G.W | G.B^T)
       float beta;
       void* d = left_dst->acc(&beta);
-      ck(ctx, nk_gemm_relu_bwd(ctx, 0, t ? 0 : 1, M, K, N, G, N, right_data->rptr(), t ? K : N, beta, d, K, gdt,
-                               left_dst->dtype, left_mask->rptr()));
+      bool summed = false;
+      if (left_colsum && beta == 0.f) {
+        float bbeta;
+        void* db = left_colsum->acc(&bbeta);
+        if (bbeta == 0.f) ck(ctx, nk_memset0(ctx, db, size_t(K) * sizeof(float)));
+        const int rc = nk_gemm_relu_bwd_colsum(ctx, 0, t ? 0 : 1, M, K, N, G, N, right_data->rptr(), t ? K : N, 0.f, d, K, gdt,
+                                               left_dst->dtype, left_mask->rptr(), static_cast<float*>(db));
+        if (rc == NK_OK)
+          summed = true;
+        else if (rc != NK_ERR_UNSUPPORTED)
+          ck(ctx, rc);
+        else if (bbeta == 0.f)
+          left_colsum->root()->is_zero = true;   // nothing was added: the plain un-broadcast below overwrites
+      }
+      if (!summed) {
+        ck(ctx, nk_gemm_relu_bwd(ctx, 0, t ? 0 : 1, M, K, N, G, N, right_data->rptr(), t ? K : N, beta, d, K, gdt,
+                                 left_dst->dtype, left_mask->rptr()));
+        if (left_colsum) {   // no fused epilogue for this shape / accumulate mode: the ordinary column sums of dZ
+          float bbeta;
+          void* db = left_colsum->acc(&bbeta);
+          const int64_t dshape[1] = {K}, gshape[2] = {M, K};
+          ck(ctx, nk_unbroadcast_acc(ctx, db, left_colsum->dtype, 1, dshape, d, left_dst->dtype, 2, gshape, bbeta));
+        }
+      }
       grad_written(left_dst);
+      grad_written(left_colsum);
     } else if (left_grad) {  // (M,K)
       float beta;
       void* d = left_grad->acc(&beta);
@@ -410,6 +437,7 @@ struct AdditionBackward : Backward {  // addition/mod.rs:52-135 (Left, Right and
   nk_ctx* ctx;
   GradientP left_grad, right_grad;
   bool left_aliased = false, right_aliased = false;  // right_aliased: the bias gradient is produced by the fused conv dW
+  bool right_fused = false;   // the bias gradient is summed in the epilogue of the dX GEMM above (MatMulBackward::left_colsum)
   const char* name() const override { return "AdditionBackward"; }
   void acc(GradientP& dst, bool aliased) {
     if (!dst || aliased) return;
@@ -421,11 +449,11 @@ struct AdditionBackward : Backward {  // addition/mod.rs:52-135 (Left, Right and
   }
   void targets(std::vector<Gradient*>& out) override {
     if (left_grad) out.push_back(left_grad->root());
-    if (right_grad) out.push_back(right_grad->root());
+    if (right_grad && !right_fused) out.push_back(right_grad->root());
   }
   void backward() override {
     acc(left_grad, left_aliased);
-    acc(right_grad, right_aliased);
+    acc(right_grad, right_aliased || right_fused);
   }
 };
 
@@ -1107,6 +1135,19 @@ void fuse(nkg_var* v) {
         mb->left_dst = rb->operand_grad;
         mb->single_pass = true;
         rb->skip = true;
+        // the Addition below the ReLU (z = x.W^T + b): its (K) row-bias gradient is the column sum of the dZ this GEMM
+        // writes -- take it in the same epilogue when it is an f32 gradient nobody else aliases
+        for (auto& kv3 : v->bwd) {
+          auto ab = std::dynamic_pointer_cast<AdditionBackward>(kv3.second);
+          if (!ab || ab->skip || ab->right_fused || ab->right_aliased || !ab->right_grad) continue;
+          if (ab->gradient.get() != rb->operand_grad.get()) continue;
+          Gradient* bg = ab->right_grad.get();
+          const Shape& gs = rb->operand_grad->shape;
+          if (bg->alias || bg->dtype != NK_F32 || gs.size() != 2 || bg->shape.size() != 1 || bg->shape[0] != gs[1]) continue;
+          mb->left_colsum = ab->right_grad;
+          ab->right_fused = true;
+          break;
+        }
         break;
       }
     }

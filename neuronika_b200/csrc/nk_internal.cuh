@@ -139,7 +139,8 @@ __device__ __forceinline__ float nk_warp_max(float v) {
 
 // engines implemented in other translation units
 int nk_gemm_simt_small_k_masked(nk_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
-                                int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype, const void* mask);
+                                int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype, int c_dtype, const void* mask,
+                                float* colsum);
 int nk_gemm_simt(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha,
                  const void* A, int64_t lda, const void* B, int64_t ldb, float beta, void* C,
                  int64_t ldc, int ab_dtype, int c_dtype, const void* bias, int bias_dtype, int relu);
@@ -147,6 +148,6 @@ int nk_gemm_simt(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int6
 // addressed by TMA, so that the caller may choose the SIMT engine
 int nk_gemm_tcgen05(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, float alpha,
                     const void* A, int64_t lda, const void* B, int64_t ldb, float beta, void* C,
-                    int64_t ldc, int c_dtype, const void* bias, int bias_dtype, int relu, const void* mask);
+                    int64_t ldc, int c_dtype, const void* bias, int bias_dtype, int relu, const void* mask, float* colsum);
 bool nk_gemm_tcgen05_supported(int transA, int transB, int64_t M, int64_t N, int64_t K,
                                const void* A, int64_t lda, const void* B, int64_t ldb);
