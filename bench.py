@@ -913,7 +913,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--sustain-s", type=float, default=1.5)
-    ap.add_argument("--fusion", type=int, default=2, choices=[0, 1, 2],
+    ap.add_argument("--fusion", type=int, default=2, choices=[0, 1, 2, 3],
                     help="host-side peephole level (nkg_set_fusion): 2 = also ReLU backward in the dX GEMM epilogue")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every step eagerly (no CUDA graph)")
     ap.add_argument("--profile", action="store_true",

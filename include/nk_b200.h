@@ -134,7 +134,8 @@ int nk_gemm_relu_bwd(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, 
 /* The same with beta = 0 and, in the same epilogue, colsum[n] += sum_m C[m][n] (N floats, f32 atomics; the caller zeroes or
  * keeps them): the bias gradient of the layer below -- the un-broadcast of its Addition's right operand,
  * addition/mod.rs:81-135 -- without a separate pass over the (M, N) gradient.  The sums are those of the values as stored
- * (after rounding to C's element type).  NK_ERR_UNSUPPORTED (nothing done) where no engine has the fused epilogue. */
+ * (after rounding to C's element type).  NK_ERR_UNSUPPORTED (nothing done) where no engine has the fused epilogue.
+ * The graph uses it at fusion level 3 (nkg_set_fusion); measured equal to the separate column-sum pass at config 4. */
 int nk_gemm_relu_bwd_colsum(nk_ctx* ctx, int transA, int transB, int64_t M, int64_t N, int64_t K, const void* A,
                             int64_t lda, const void* B, int64_t ldb, float beta, void* C, int64_t ldc, int ab_dtype,
                             int c_dtype, const void* relu_operand, float* colsum);

@@ -188,20 +188,33 @@ __device__ __forceinline__ void scale_and_bias(const GemmParams& p, int64_t row,
 // zero.  A butterfly of 31 shuffles leaves the sum of column j on lane j; one atomic per column and chunk.
 template <typename TC>
 __device__ __forceinline__ void epilogue_colsum_chunk32(const GemmParams& p, int64_t row, int64_t col0, const uint32_t* r,
-                                                        int lane) {
+                                                        int lane, bool vec_ok) {
   float v[32];
   const bool live = row < p.M;
   const TC* mrow = (p.mask && live) ? static_cast<const TC*>(p.mask) + row * p.ldc + col0 : nullptr;
+  const bool full = col0 + 32 <= p.N;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float x = 0.f;
-    if (live && col0 + j < p.N) {
-      x = p.alpha * __uint_as_float(r[j]);
-      if (mrow) x = nk_to_f32<TC>(mrow[j]) > 0.f ? x : 0.f;
-      x = nk_to_f32<TC>(nk_from_f32<TC>(x));   // what the output tensor will hold
+  for (int j = 0; j < 32; ++j) v[j] = (live && col0 + j < p.N) ? p.alpha * __uint_as_float(r[j]) : 0.f;
+  if (mrow) {
+    if (full && vec_ok) {
+      // the same four 16-byte loads per row the store path issues right after (then L1 hits): 32 scalar loads per row,
+      // each a first touch of the mask, made the epilogue of an 8192 x 4096 GEMM longer than its main loop
+      constexpr int V = 16 / sizeof(TC);
+#pragma unroll
+      for (int q = 0; q < 32 / V; ++q) {
+        NkVec<TC> mk;
+        mk.load(mrow + q * V);
+#pragma unroll
+        for (int i = 0; i < V; ++i) v[q * V + i] = mk.get(i) > 0.f ? v[q * V + i] : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] = nk_to_f32<TC>(mrow[j]) > 0.f ? v[j] : 0.f;
     }
-    v[j] = x;
   }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = nk_to_f32<TC>(nk_from_f32<TC>(v[j]));   // what the output tensor will hold
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     const bool upper = (lane & off) != 0;
@@ -678,7 +691,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               continue;
             }
           }
-          if (p.colsum && col0 < p.N) epilogue_colsum_chunk32<TC>(p, row, col0, r, lane);
+          if (p.colsum && col0 < p.N) epilogue_colsum_chunk32<TC>(p, row, col0, r, lane, vec_ok);
           if (row < p.M && col0 < p.N) epilogue_store_chunk32<TC>(p, row, col0, r, 32, vec_ok, c_off, atomic);
         }
       } else {

@@ -31,7 +31,7 @@ namespace nkg {
 
 static thread_local std::string g_error;
 static int g_fusion = 1;  // 0 off, 1 exact for any use of the tape, 2 additionally assumes ONE backward() per tape,
-                          // 3 = 2 + the bias-gradient column sums in the dX GEMM epilogue (measured slower: see fuse())
+                          // 3 = 2 + the bias-gradient column sums in the dX GEMM epilogue (no measured gain: see fuse())
 static uint64_t g_next_op_id = 1;  // creation order == a topological order (history.rs:84-88)
 
 struct Error : std::runtime_error {
@@ -1138,9 +1138,9 @@ void fuse(nkg_var* v) {
         rb->skip = true;
         // the Addition below the ReLU (z = x.W^T + b): its (K) row-bias gradient is the column sum of the dZ this GEMM
         // writes -- take it in the same epilogue when it is an f32 gradient nobody else aliases.  LEVEL 3 ONLY: correct
-        // (the GPU suite runs it), but at config 4 the step went 0.79 -> 1.00 ms: the butterfly + a second read of the
-        // mask make the epilogue of the 8192 x 4096 GEMM longer than its main loop, and 1.3 M f32 atomics land on 4096
-        // addresses.  Needs the sums folded into the store path's registers and one atomic per column and CTA first.
+        // (the GPU suite runs it) and four launches fewer per config-4 step, but no faster: 0.791 vs 0.793 ms -- the
+        // butterfly and the 1.3 M f32 atomics cost what the two column-sum passes did (a first version with scalar mask
+        // loads was 0.2 ms SLOWER: its epilogue outlasted the main loop).  One atomic per column and CTA would be next.
         for (auto& kv3 : v->bwd) {
           if (g_fusion < 3) break;
           auto ab = std::dynamic_pointer_cast<AdditionBackward>(kv3.second);
