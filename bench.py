@@ -19,8 +19,9 @@ workload has them) through the package's public API (Var/VarDiff/nn/optim over t
 is recorded ONCE into a CUDA graph (Device.capture; the tape is the same every iteration) and replayed with one driver
 call per step; `eager_ms_per_step` reports the same step enqueued kernel by kernel.  `value` times the steps with
 inputs resident in HBM; `e2e` repeats them with the step's inputs copied from pinned host memory and the loss read back
-inside the timed region.  The default workload is `value`; the other two configs are measured in the same process and
-reported under `other_configs` (config 4 is the strong-scaling curve north_star asks for).  One JSON line, rank 0.
+inside the timed region.  The default workload is `value`; the other three GPU configs are measured in the same process
+and reported under `other_configs` (config 4 is the strong-scaling curve north_star asks for).  N > 1 adds
+`exchange_parity`: the fused NVLink exchange against an NCCL all-reduce of locally computed gradients.  One JSON line, rank 0.
 """
 from __future__ import annotations
 
